@@ -1,0 +1,207 @@
+/*
+ * sfgs.h — C ABI of the B200-native splat rasterizer (libsfgs.so).
+ *
+ * Drop-in boundary for the hot path of jayin92/Skyfall-GS: every entry point
+ * below replaces one entry of the reference's native interface.  Citations
+ * are to the reference tree (RAST = submodules/diff-gaussian-rasterization-depth,
+ * SSIM = submodules/fused-ssim, KNN = submodules/simple-knn):
+ *
+ *   sfgs_rasterize_forward   <- CudaRasterizer::Rasterizer::forward
+ *                               RAST/cuda_rasterizer/rasterizer.h:35-68
+ *                               (bound by RasterizeGaussiansCUDA, RAST/rasterize_points.cu:35-135)
+ *   sfgs_rasterize_backward  <- CudaRasterizer::Rasterizer::backward
+ *                               RAST/cuda_rasterizer/rasterizer.h:70-103
+ *                               (bound by RasterizeGaussiansBackwardCUDA, RAST/rasterize_points.cu:137-243)
+ *   sfgs_mark_visible        <- CudaRasterizer::Rasterizer::markVisible
+ *                               RAST/cuda_rasterizer/rasterizer.h:23-33 (RAST/rasterize_points.cu:245-264)
+ *   sfgs_fusedssim_forward   <- fusedssim          SSIM/ssim.h:7-14
+ *   sfgs_fusedssim_backward  <- fusedssim_backward SSIM/ssim.h:16-26
+ *   sfgs_dist2_knn3          <- SimpleKNN::knn     KNN/simple_knn.h (bound by distCUDA2, KNN/spatial.cu:17-35)
+ *
+ * Conventions: plain C, raw DEVICE pointers (unless a name ends in _host),
+ * sizes as int/size_t, a CUDA stream passed as void* (cudaStream_t), int
+ * status returns (0 / >=0 = success, <0 = SFGS_E_*), no C++ exceptions and no
+ * torch types cross this boundary.  All matrices use the reference's layout:
+ * viewmatrix[16]/projmatrix[16] are the row-vector ("transposed") tensors of
+ * scene/cameras.py:64-73, i.e. element [4*c + r].
+ *
+ * Scratch memory is obtained through caller-supplied allocator callbacks, the
+ * C equivalent of the reference's std::function<char*(size_t)> resize
+ * callbacks (RAST/rasterize_points.cu:27-33).  A callback may be invoked more
+ * than once per call (the last returned pointer is the live one) and the
+ * memory must stay valid until the matching backward call has run.
+ */
+#ifndef SFGS_H_INCLUDED
+#define SFGS_H_INCLUDED
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SFGS_VERSION 1
+#define SFGS_TILE 16          /* BLOCK_X = BLOCK_Y = 16, RAST/cuda_rasterizer/config.h:15-17 */
+#define SFGS_MAX_EXTRA 34     /* MAX_EXTRA_DIMS, RAST/cuda_rasterizer/auxiliary.h:20 */
+
+enum {
+  SFGS_OK = 0,
+  SFGS_E_CUDA = -1,        /* a CUDA runtime call failed; sfgs_last_error() has the text */
+  SFGS_E_BADARG = -2,      /* null pointer / bad size / unsupported combination */
+  SFGS_E_ALLOC = -3,       /* an allocator callback returned NULL */
+  SFGS_E_UNSUPPORTED = -4  /* feature of the reference API not implemented by this build */
+};
+
+/* Allocator callback: return a device pointer to at least `bytes` bytes
+ * (256-byte aligned), or NULL on failure. */
+typedef char* (*sfgs_alloc_fn)(void* user, size_t bytes);
+
+/* ---- rasterizer forward ------------------------------------------------ */
+typedef struct sfgs_forward_args {
+  /* scratch: geometry (per Gaussian), binning (per tile instance), image (per pixel / tile) */
+  sfgs_alloc_fn geom_alloc;    void* geom_user;
+  sfgs_alloc_fn binning_alloc; void* binning_user;
+  sfgs_alloc_fn image_alloc;   void* image_user;
+  int P;                 /* number of Gaussians */
+  int D;                 /* active SH degree (0..3) */
+  int M;                 /* SH coefficients per Gaussian in `shs` (0 when colors_precomp is used) */
+  int ED;                /* extra attribute channels (0..34) */
+  int width, height;
+  const float* background;      /* [3] */
+  const float* means3D;         /* [P,3] */
+  const float* shs;             /* [P,M,3] or NULL */
+  const float* colors_precomp;  /* [P,3] or NULL */
+  const float* opacities;       /* [P] */
+  const float* scales;          /* [P,3] */
+  float scale_modifier;
+  const float* rotations;       /* [P,4] (w,x,y,z), used as given (not re-normalised) */
+  const float* cov3D_precomp;   /* [P,6] or NULL */
+  const float* norm3D_precomp;  /* [P,3] or NULL */
+  const float* extra_attrs;     /* [P,ED] or NULL */
+  const float* viewmatrix;      /* [16] */
+  const float* projmatrix;      /* [16] */
+  const float* cam_pos;         /* [3] */
+  float tan_fovx, tan_fovy;
+  float kernel_size;
+  int prefiltered;
+  /* outputs (every element is written; no pre-zeroing required) */
+  float* out_color;   /* [3,H,W] */
+  float* out_depth;   /* [1,H,W] */
+  float* out_norm;    /* [3,H,W] (un-normalised, as the reference) */
+  float* out_alpha;   /* [1,H,W] */
+  float* out_extra;   /* [ED,H,W] or NULL */
+  int*   radii;       /* [P] */
+  int debug;          /* synchronise and check after every stage */
+  void* stream;       /* cudaStream_t */
+  /* optional hint: expected number of tile instances (0 = let the library guess) */
+  long long capacity_hint;
+} sfgs_forward_args;
+
+/* Returns num_rendered (>= 0) or a negative SFGS_E_* code. */
+int sfgs_rasterize_forward(const sfgs_forward_args* a);
+
+/* ---- rasterizer backward ----------------------------------------------- */
+typedef struct sfgs_backward_args {
+  int P, D, M, R, ED;
+  int width, height;
+  const float* background;
+  const float* means3D;
+  const float* shs;
+  const float* colors_precomp;
+  const float* scales;
+  float scale_modifier;
+  const float* rotations;
+  const float* cov3D_precomp;
+  const float* norm3D_precomp;
+  const float* extra_attrs;
+  const float* viewmatrix;
+  const float* projmatrix;
+  const float* cam_pos;
+  float tan_fovx, tan_fovy;
+  float kernel_size;
+  const int* radii;
+  char* geom_buffer;       /* the live pointers handed out by the forward allocators */
+  char* binning_buffer;
+  char* image_buffer;
+  const float* accum_alphas;   /* out_alpha of the forward */
+  const float* dL_dpix;        /* [3,H,W] */
+  const float* dL_dpix_depth;  /* [1,H,W] */
+  const float* dL_dpix_norm;   /* [3,H,W] */
+  const float* dL_dpix_alpha;  /* [1,H,W] */
+  const float* dL_dpix_extra;  /* [ED,H,W] or NULL */
+  /* outputs: every element is written by the call (no pre-zeroing required) */
+  float* dL_dmean2D;   /* [P,3]  (x*W/2, y*H/2, sum|.|) */
+  float* dL_dconic;    /* [P,4]  (xx, xy, unused, yy) */
+  float* dL_dopacity;  /* [P] */
+  float* dL_dcolor;    /* [P,3] */
+  float* dL_ddepth;    /* [P] */
+  float* dL_dmean3D;   /* [P,3] */
+  float* dL_dcov3D;    /* [P,6] */
+  float* dL_dnorm3D;   /* [P,3] */
+  float* dL_dsh;       /* [P,M,3] or NULL when M == 0 */
+  float* dL_dscale;    /* [P,3] */
+  float* dL_drot;      /* [P,4] */
+  float* dL_dextra;    /* [P,ED] or NULL */
+  /* scratch for the per-Gaussian blend-adjoint accumulators: P*16 floats, need not be zeroed */
+  sfgs_alloc_fn scratch_alloc; void* scratch_user;
+  int debug;
+  void* stream;
+} sfgs_backward_args;
+
+int sfgs_rasterize_backward(const sfgs_backward_args* a);
+
+/* ---- markVisible --------------------------------------------------------- */
+int sfgs_mark_visible(int P, const float* means3D, const float* viewmatrix,
+                      const float* projmatrix, unsigned char* present, void* stream);
+
+/* ---- introspection of the opaque scratch buffers (used by the parity tests) */
+typedef struct sfgs_geom_view {
+  const float* rec;            /* [P,16] packed blend record: mx,my, conic.x,.y,.z, opac*coef, depth, pad, r,g,b, nx,ny,nz, pad,pad */
+  const float* cov3D;          /* [P,6] */
+  const unsigned char* clamped;/* [P] bit0..2 = r,g,b clamped */
+  const uint32_t* tiles_touched; /* [P] */
+} sfgs_geom_view;
+typedef struct sfgs_image_view {
+  const uint32_t* n_contrib;   /* [H*W] */
+  const uint32_t* ranges;      /* [tiles,2] (start,end) into point_list */
+  const uint32_t* tile_count;  /* [tiles] */
+} sfgs_image_view;
+typedef struct sfgs_binning_view {
+  const uint64_t* keys;        /* [R] (depth_bits<<32 | gaussian) grouped by tile, sorted inside each tile */
+  const uint32_t* point_list;  /* [R] sorted Gaussian ids */
+} sfgs_binning_view;
+size_t sfgs_geom_bytes(int P);
+size_t sfgs_image_bytes(int width, int height);
+size_t sfgs_binning_bytes(long long capacity);
+int sfgs_geom_layout(char* base, int P, sfgs_geom_view* out);
+int sfgs_image_layout(char* base, int width, int height, sfgs_image_view* out);
+int sfgs_binning_layout(char* base, long long capacity, sfgs_binning_view* out);
+/* capacity (in tile instances) the last forward on this buffer was sized for; stored in the image buffer header */
+long long sfgs_last_capacity(void);
+
+/* ---- fused SSIM ---------------------------------------------------------- */
+int sfgs_fusedssim_forward(float C1, float C2, int B, int CH, int H, int W,
+                           const float* img1, const float* img2, int train,
+                           float* ssim_map, float* dm_dmu1, float* dm_dsigma1_sq,
+                           float* dm_dsigma12, void* stream);
+int sfgs_fusedssim_backward(float C1, float C2, int B, int CH, int H, int W,
+                            const float* img1, const float* img2, const float* dL_dmap,
+                            const float* dm_dmu1, const float* dm_dsigma1_sq,
+                            const float* dm_dsigma12, float* dL_dimg1, void* stream);
+
+/* ---- simple-knn ---------------------------------------------------------- */
+/* mean squared distance to the 3 nearest neighbours; scratch via callback */
+int sfgs_dist2_knn3(int P, const float* points, float* mean_dist2,
+                    sfgs_alloc_fn scratch_alloc, void* scratch_user, void* stream);
+
+/* ---- misc ---------------------------------------------------------------- */
+const char* sfgs_last_error(void);
+int sfgs_version(void);
+/* number of kernel launches issued by this library since load (for bench.py's gpu_launches) */
+long long sfgs_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SFGS_H_INCLUDED */

@@ -1,0 +1,239 @@
+// sfgs_api.cu — C ABI entry points (see include/sfgs.h) and stage orchestration.
+//
+// Forward  = zero tile histogram -> preprocess -> tile scan -> key emission ->
+//            per-tile sort -> blend, all queued on the caller's stream with no
+//            host round trip in between; the only synchronisation is the read
+//            of num_rendered at the very end (the reference blocks on a
+//            cudaMemcpy in the middle of its forward, rasterizer_impl.cu:286-287,
+//            because it must size the binning buffer before it can continue).
+//            The binning buffer is sized from a running estimate instead and the
+//            tail of the pipeline is re-run in the rare case it was too small.
+// Backward = zero accumulators -> tile blend adjoint -> per-Gaussian adjoint.
+#include <cstdio>
+#include <cstring>
+#include <atomic>
+#include <mutex>
+#include "sfgs_common.cuh"
+
+long long g_sfgs_launches = 0;
+
+void sfgs_launch_preprocess(const sfgs_forward_args* a, const GeomLayout& g, const ImageLayout& im, float focal_x,
+                            float focal_y, cudaStream_t st);
+void sfgs_launch_mark_visible(int P, const float* means3D, const float* viewmatrix, unsigned char* present,
+                              cudaStream_t st);
+void sfgs_launch_tile_scan(const ImageLayout& im, unsigned long long capacity, cudaStream_t st);
+void sfgs_launch_emit(int P, const int* radii, const GeomLayout& g, const ImageLayout& im, const BinningLayout& b,
+                      cudaStream_t st);
+void sfgs_launch_tile_sort(const ImageLayout& im, const BinningLayout& b, cudaStream_t st);
+void sfgs_launch_render_fwd(const sfgs_forward_args* a, const GeomLayout& g, const ImageLayout& im,
+                            const BinningLayout& b, cudaStream_t st);
+void sfgs_launch_render_bwd(const sfgs_backward_args* a, const GeomLayout& g, const ImageLayout& im,
+                            const BinningLayout& b, float* acc, cudaStream_t st);
+void sfgs_launch_gauss_bwd(const sfgs_backward_args* a, const GeomLayout& g, float focal_x, float focal_y,
+                           const float* acc, cudaStream_t st);
+
+namespace {
+
+thread_local char t_err[512] = "";
+std::atomic<long long> g_last_R{0};
+std::atomic<long long> g_last_capacity{0};
+
+int fail(int code, const char* what, cudaError_t e = cudaSuccess) {
+  if (e != cudaSuccess) snprintf(t_err, sizeof(t_err), "%s: %s", what, cudaGetErrorString(e));
+  else snprintf(t_err, sizeof(t_err), "%s", what);
+  return code;
+}
+
+#define CU(call)                                                   \
+  do {                                                             \
+    cudaError_t _e = (call);                                       \
+    if (_e != cudaSuccess) return fail(SFGS_E_CUDA, #call, _e);    \
+  } while (0)
+
+#define STAGE_CHECK(name)                                                              \
+  do {                                                                                 \
+    cudaError_t _e = cudaGetLastError();                                               \
+    if (_e != cudaSuccess) return fail(SFGS_E_CUDA, "launch " name, _e);               \
+    if (debug) {                                                                       \
+      _e = cudaStreamSynchronize(st);                                                  \
+      if (_e != cudaSuccess) return fail(SFGS_E_CUDA, "stage " name, _e);              \
+    }                                                                                  \
+  } while (0)
+
+struct PinnedHdr {
+  uint32_t* p = nullptr;
+  ~PinnedHdr() { /* leaked on purpose: the CUDA context may already be gone at exit */ }
+  uint32_t* get() {
+    if (!p) { if (cudaHostAlloc((void**)&p, IMG_HDR_WORDS * sizeof(uint32_t), cudaHostAllocDefault) != cudaSuccess) p = nullptr; }
+    return p;
+  }
+};
+thread_local PinnedHdr t_hdr;
+
+}  // namespace
+
+extern "C" {
+
+const char* sfgs_last_error(void) { return t_err; }
+int sfgs_version(void) { return SFGS_VERSION; }
+long long sfgs_launch_count(void) { return g_sfgs_launches; }
+long long sfgs_last_capacity(void) { return g_last_capacity.load(); }
+
+size_t sfgs_geom_bytes(int P) { return GeomLayout(nullptr, (size_t)(P > 0 ? P : 0)).bytes; }
+size_t sfgs_image_bytes(int width, int height) { return ImageLayout(nullptr, width, height).bytes; }
+size_t sfgs_binning_bytes(long long capacity) { return BinningLayout(nullptr, (size_t)(capacity > 0 ? capacity : 0)).bytes; }
+
+int sfgs_geom_layout(char* base, int P, sfgs_geom_view* out) {
+  if (!base || !out) return fail(SFGS_E_BADARG, "sfgs_geom_layout: null");
+  GeomLayout g(sfgs_align_ptr(base), (size_t)P);
+  out->rec = g.rec; out->cov3D = g.cov3D; out->clamped = g.clamped; out->tiles_touched = g.tiles_touched;
+  return SFGS_OK;
+}
+int sfgs_image_layout(char* base, int width, int height, sfgs_image_view* out) {
+  if (!base || !out) return fail(SFGS_E_BADARG, "sfgs_image_layout: null");
+  ImageLayout im(sfgs_align_ptr(base), width, height);
+  out->n_contrib = im.n_contrib; out->ranges = (const uint32_t*)im.ranges; out->tile_count = im.tile_count;
+  return SFGS_OK;
+}
+int sfgs_binning_layout(char* base, long long capacity, sfgs_binning_view* out) {
+  if (!base || !out) return fail(SFGS_E_BADARG, "sfgs_binning_layout: null");
+  BinningLayout b(sfgs_align_ptr(base), (size_t)capacity);
+  out->keys = b.keys; out->point_list = b.point_list;
+  return SFGS_OK;
+}
+
+int sfgs_rasterize_forward(const sfgs_forward_args* a) {
+  if (!a) return fail(SFGS_E_BADARG, "forward: null args");
+  if (a->P < 0 || a->width <= 0 || a->height <= 0) return fail(SFGS_E_BADARG, "forward: bad sizes");
+  if (a->ED < 0 || a->ED > SFGS_MAX_EXTRA) return fail(SFGS_E_BADARG, "forward: ED out of range");
+  if (!a->out_color || !a->out_depth || !a->out_norm || !a->out_alpha || (a->P > 0 && !a->radii))
+    return fail(SFGS_E_BADARG, "forward: null output");
+  if (!a->geom_alloc || !a->binning_alloc || !a->image_alloc) return fail(SFGS_E_BADARG, "forward: null allocator");
+  if (a->P > 0) {
+    if (!a->means3D || !a->opacities || !a->viewmatrix || !a->projmatrix || !a->cam_pos || !a->background)
+      return fail(SFGS_E_BADARG, "forward: null input");
+    if (!a->shs && !a->colors_precomp) return fail(SFGS_E_BADARG, "forward: need shs or colors_precomp");
+    if (a->colors_precomp == nullptr && (a->M <= 0 || a->D < 0 || a->D > 3 || (a->D + 1) * (a->D + 1) > a->M))
+      return fail(SFGS_E_BADARG, "forward: SH degree/M mismatch");
+    if (!a->cov3D_precomp && (!a->scales || !a->rotations)) return fail(SFGS_E_BADARG, "forward: need scales+rotations or cov3D_precomp");
+    if (!a->norm3D_precomp && (!a->scales || !a->rotations)) return fail(SFGS_E_BADARG, "forward: need scales+rotations or norm3D_precomp");
+    if (a->ED > 0 && (!a->extra_attrs || !a->out_extra)) return fail(SFGS_E_BADARG, "forward: extra attrs missing");
+  }
+  cudaStream_t st = (cudaStream_t)a->stream;
+  const bool debug = a->debug != 0;
+  const int P = a->P;
+
+  const float focal_y = a->height / (2.0f * a->tan_fovy);
+  const float focal_x = a->width / (2.0f * a->tan_fovx);
+
+  const size_t gbytes = GeomLayout(nullptr, (size_t)P).bytes;
+  char* gptr = a->geom_alloc(a->geom_user, gbytes);
+  if (!gptr) return fail(SFGS_E_ALLOC, "forward: geometry allocator returned NULL");
+  GeomLayout g(sfgs_align_ptr(gptr), (size_t)P);
+
+  const size_t ibytes = ImageLayout(nullptr, a->width, a->height).bytes;
+  char* iptr = a->image_alloc(a->image_user, ibytes);
+  if (!iptr) return fail(SFGS_E_ALLOC, "forward: image allocator returned NULL");
+  ImageLayout im(sfgs_align_ptr(iptr), a->width, a->height);
+
+  // tile histogram + header start at zero
+  CU(cudaMemsetAsync(im.hdr, 0, IMG_HDR_WORDS * sizeof(uint32_t), st));
+  CU(cudaMemsetAsync(im.tile_count, 0, (size_t)im.tiles * sizeof(uint32_t), st));
+
+  if (P > 0) {
+    sfgs_launch_preprocess(a, g, im, focal_x, focal_y, st);
+    STAGE_CHECK("preprocess");
+  }
+
+  long long capacity = a->capacity_hint;
+  if (capacity <= 0) {
+    const long long last = g_last_R.load();
+    capacity = last > 0 ? last + last / 4 + 4096 : (long long)P * 4 + 65536;
+  }
+  uint32_t* hhdr = t_hdr.get();
+  if (!hhdr) return fail(SFGS_E_CUDA, "forward: pinned header allocation failed");
+
+  long long R = 0;
+  for (int attempt = 0; attempt < 3; attempt++) {
+    const size_t bbytes = BinningLayout(nullptr, (size_t)capacity).bytes;
+    char* bptr = a->binning_alloc(a->binning_user, bbytes);
+    if (!bptr) return fail(SFGS_E_ALLOC, "forward: binning allocator returned NULL");
+    BinningLayout b(sfgs_align_ptr(bptr), (size_t)capacity);
+
+    sfgs_launch_tile_scan(im, (unsigned long long)capacity, st);
+    STAGE_CHECK("tile_scan");
+    if (P > 0) {
+      sfgs_launch_emit(P, a->radii, g, im, b, st);
+      STAGE_CHECK("emit_keys");
+      sfgs_launch_tile_sort(im, b, st);
+      STAGE_CHECK("tile_sort");
+    }
+    sfgs_launch_render_fwd(a, g, im, b, st);
+    STAGE_CHECK("render_fwd");
+
+    CU(cudaMemcpyAsync(hhdr, im.hdr, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    R = (long long)hhdr[HDR_R];
+    if (!hhdr[HDR_OVERFLOW]) break;
+    if (attempt == 2) return fail(SFGS_E_CUDA, "forward: binning capacity overflow persisted");
+    capacity = R + R / 16 + 4096;   // exact count is now known; re-run the tail of the pipeline
+  }
+  g_last_R.store(R);
+  g_last_capacity.store(capacity);
+  return (int)R;
+}
+
+int sfgs_rasterize_backward(const sfgs_backward_args* a) {
+  if (!a) return fail(SFGS_E_BADARG, "backward: null args");
+  if (a->P < 0 || a->width <= 0 || a->height <= 0) return fail(SFGS_E_BADARG, "backward: bad sizes");
+  if (a->P == 0) return SFGS_OK;
+  if (!a->geom_buffer || !a->binning_buffer || !a->image_buffer) return fail(SFGS_E_BADARG, "backward: null scratch buffer");
+  if (!a->dL_dpix || !a->dL_dpix_depth || !a->dL_dpix_norm || !a->dL_dpix_alpha || !a->accum_alphas)
+    return fail(SFGS_E_BADARG, "backward: null pixel gradient");
+  if (!a->dL_dmean2D || !a->dL_dconic || !a->dL_dopacity || !a->dL_dcolor || !a->dL_ddepth || !a->dL_dmean3D ||
+      !a->dL_dcov3D || !a->dL_dnorm3D || !a->dL_dscale || !a->dL_drot)
+    return fail(SFGS_E_BADARG, "backward: null output");
+  if (a->M > 0 && a->shs && !a->dL_dsh) return fail(SFGS_E_BADARG, "backward: dL_dsh missing");
+  if (a->ED > 0 && (!a->dL_dextra || !a->dL_dpix_extra || !a->extra_attrs)) return fail(SFGS_E_BADARG, "backward: extra attrs missing");
+  if (!a->scratch_alloc) return fail(SFGS_E_BADARG, "backward: null scratch allocator");
+  cudaStream_t st = (cudaStream_t)a->stream;
+  const bool debug = a->debug != 0;
+  const int P = a->P;
+
+  GeomLayout g(sfgs_align_ptr(a->geom_buffer), (size_t)P);
+  ImageLayout im(sfgs_align_ptr(a->image_buffer), a->width, a->height);
+  // only point_list is needed; it sits at the head of the layout irrespective of the capacity
+  BinningLayout b(sfgs_align_ptr(a->binning_buffer), (size_t)(a->R > 0 ? a->R : 0));
+
+  const float focal_y = a->height / (2.0f * a->tan_fovy);
+  const float focal_x = a->width / (2.0f * a->tan_fovx);
+
+  const size_t abytes = (size_t)P * 16 * sizeof(float) + SFGS_ALIGN;
+  char* aptr = a->scratch_alloc(a->scratch_user, abytes);
+  if (!aptr) return fail(SFGS_E_ALLOC, "backward: scratch allocator returned NULL");
+  float* acc = (float*)sfgs_align_ptr(aptr);
+  CU(cudaMemsetAsync(acc, 0, (size_t)P * 16 * sizeof(float), st));
+  if (a->ED > 0) CU(cudaMemsetAsync(a->dL_dextra, 0, (size_t)P * a->ED * sizeof(float), st));
+
+  if (a->R > 0) {
+    sfgs_launch_render_bwd(a, g, im, b, acc, st);
+    STAGE_CHECK("render_bwd");
+  }
+  sfgs_launch_gauss_bwd(a, g, focal_x, focal_y, acc, st);
+  STAGE_CHECK("gauss_bwd");
+  return SFGS_OK;
+}
+
+int sfgs_mark_visible(int P, const float* means3D, const float* viewmatrix, const float* projmatrix,
+                      unsigned char* present, void* stream) {
+  (void)projmatrix;   // the reference's test only uses the view depth (auxiliary.h:155)
+  if (P < 0) return fail(SFGS_E_BADARG, "mark_visible: P < 0");
+  if (P == 0) return SFGS_OK;
+  if (!means3D || !viewmatrix || !present) return fail(SFGS_E_BADARG, "mark_visible: null");
+  sfgs_launch_mark_visible(P, means3D, viewmatrix, present, (cudaStream_t)stream);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(SFGS_E_CUDA, "mark_visible", e);
+  return SFGS_OK;
+}
+
+}  // extern "C"

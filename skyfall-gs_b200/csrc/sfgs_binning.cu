@@ -1,0 +1,206 @@
+// sfgs_binning.cu — tile binning: histogram scan, key emission, per-tile sort.
+//
+// Replaces cub::DeviceScan::InclusiveSum + duplicateWithKeys +
+// cub::DeviceRadixSort::SortPairs + identifyTileRanges
+// (RAST/cuda_rasterizer/rasterizer_impl.cu:70-138, 283-324).
+//
+// The reference sorts all R (tile|depth) 64-bit keys globally with a stable
+// LSD radix sort, so inside a tile equal depths keep emission order = ascending
+// Gaussian id.  Here the tile part of the key is resolved by a counting sort
+// (per-tile histogram from the preprocess stage -> exclusive scan -> bucket
+// cursors) and each tile bucket is then sorted on (depth_bits << 32 | id) in
+// shared memory.  The resulting (tile, depth, id) order — and therefore
+// point_list and ranges — is identical to the reference's, bit for bit.
+#include "sfgs_common.cuh"
+
+namespace {
+
+// ---- exclusive scan of the tile histogram (single CTA) ----------------------
+constexpr int SCAN_THREADS = 1024;
+__global__ void __launch_bounds__(SCAN_THREADS)
+tile_scan_kernel(int tiles, const uint32_t* __restrict__ tile_count, uint2* __restrict__ ranges,
+                 uint32_t* __restrict__ tile_cursor, uint32_t* __restrict__ hdr, unsigned long long capacity) {
+  __shared__ uint32_t warp_sums[32];
+  __shared__ uint32_t carry_s;
+  __shared__ uint32_t maxlen_s;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  if (tid == 0) { carry_s = 0; maxlen_s = 0; }
+  __syncthreads();
+  uint32_t local_max = 0;
+  for (int base = 0; base < tiles; base += SCAN_THREADS) {
+    const int i = base + tid;
+    const uint32_t v = (i < tiles) ? tile_count[i] : 0u;
+    local_max = max(local_max, v);
+    uint32_t x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+    if (lane == 31) warp_sums[wid] = x;
+    __syncthreads();
+    if (wid == 0) {
+      uint32_t s = warp_sums[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, s, o); if (lane >= o) s += y; }
+      warp_sums[lane] = s;
+    }
+    __syncthreads();
+    const uint32_t carry = carry_s;
+    const uint32_t incl = carry + x + (wid > 0 ? warp_sums[wid - 1] : 0u);
+    if (i < tiles) {
+      // empty tiles read (0,0) exactly like the reference's memset + identifyTileRanges
+      ranges[i] = v ? make_uint2(incl - v, incl) : make_uint2(0u, 0u);
+      tile_cursor[i] = 0u;
+    }
+    __syncthreads();
+    if (tid == SCAN_THREADS - 1) carry_s = incl;
+    __syncthreads();
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) local_max = max(local_max, __shfl_xor_sync(0xffffffffu, local_max, o));
+  if (lane == 0) atomicMax(&maxlen_s, local_max);
+  __syncthreads();
+  if (tid == 0) {
+    const uint32_t R = carry_s;
+    hdr[HDR_R] = R;
+    hdr[HDR_OVERFLOW] = ((unsigned long long)R > capacity) ? 1u : 0u;
+    hdr[HDR_MAXTILE] = maxlen_s;
+  }
+}
+
+// ---- key emission ------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+emit_keys_kernel(int P, const int* __restrict__ radii, const float* __restrict__ rec, int gx, int gy,
+                 const uint2* __restrict__ ranges, uint32_t* __restrict__ tile_cursor,
+                 const uint32_t* __restrict__ hdr, uint64_t* __restrict__ keys) {
+  if (hdr[HDR_OVERFLOW]) return;
+  const int idx = blockIdx.x * 256 + threadIdx.x;
+  if (idx >= P) return;
+  const int radius = radii[idx];
+  if (radius <= 0) return;
+  const float4 r0 = *reinterpret_cast<const float4*>(rec + (size_t)idx * REC_FLOATS);
+  const float depth = rec[(size_t)idx * REC_FLOATS + REC_DEPTH];
+  const TileRect r = tile_rect(r0.x, r0.y, radius, gx, gy);
+  const uint64_t key = ((uint64_t)__float_as_uint(depth) << 32) | (uint32_t)idx;
+  for (int y = r.y0; y < r.y1; y++)
+    for (int x = r.x0; x < r.x1; x++) {
+      const int t = y * gx + x;
+      const uint32_t pos = atomicAdd(&tile_cursor[t], 1u);
+      keys[ranges[t].x + pos] = key;
+    }
+}
+
+// ---- per-tile sort -------------------------------------------------------------
+// One CTA per tile. Lists that fit the shared-memory window are sorted with a
+// bitonic network on 64-bit keys (padded with ~0); longer lists fall back to an
+// in-CTA LSD radix sort that ping-pongs through global memory.
+constexpr int SORT_THREADS = 256;
+constexpr int SORT_SMEM_KEYS = 4096;   // 32 KB window
+
+__device__ __forceinline__ void bitonic_smem(uint64_t* s, int n2) {
+  for (int k = 2; k <= n2; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < n2; i += SORT_THREADS) {
+        const int l = i ^ j;
+        if (l > i) {
+          const uint64_t a = s[i], b = s[l];
+          const bool up = ((i & k) == 0);
+          if ((a > b) == up) { s[i] = b; s[l] = a; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// stable LSD radix sort of n 64-bit keys, 8 bits per pass, one CTA, global ping-pong
+__device__ void radix_global(uint64_t* a, uint64_t* b, int n) {
+  __shared__ uint32_t hist[256];
+  __shared__ uint32_t digit_base[256];
+  __shared__ uint32_t warp_digit_cnt[SORT_THREADS / 32][256];  // 8 KB
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  uint64_t* src = a; uint64_t* dst = b;
+  for (int pass = 0; pass < 8; pass++) {
+    const int shift = pass * 8;
+    hist[tid] = 0;   // SORT_THREADS == 256
+    __syncthreads();
+    for (int i = tid; i < n; i += SORT_THREADS) atomicAdd(&hist[(src[i] >> shift) & 255u], 1u);
+    __syncthreads();
+    // skip passes whose digit is constant over the bucket
+    __shared__ int skip;
+    if (tid == 0) skip = 0;
+    __syncthreads();
+    if (hist[tid] == (uint32_t)n) skip = 1;
+    __syncthreads();
+    if (skip) { __syncthreads(); continue; }
+    if (tid == 0) { uint32_t s = 0; for (int d = 0; d < 256; d++) { digit_base[d] = s; s += hist[d]; } }
+    __syncthreads();
+    for (int base = 0; base < n; base += SORT_THREADS) {
+      for (int d = lane; d < 256; d += 32) warp_digit_cnt[wid][d] = 0;
+      __syncwarp();
+      const int i = base + tid;
+      const bool valid = i < n;
+      uint64_t key = valid ? src[i] : 0;
+      const uint32_t d = (uint32_t)(key >> shift) & 255u;
+      // rank among earlier lanes of this warp with the same digit
+      const unsigned peers = __match_any_sync(0xffffffffu, valid ? d : 0xffffffffu);
+      const uint32_t rank_in_warp = __popc(peers & ((1u << lane) - 1u));
+      if (valid && rank_in_warp == 0) warp_digit_cnt[wid][d] = __popc(peers);
+      __syncthreads();
+      // exclusive prefix over warps for my digit
+      uint32_t before = 0;
+      if (valid) for (int w = 0; w < wid; w++) before += warp_digit_cnt[w][d];
+      if (valid) dst[digit_base[d] + before + rank_in_warp] = key;
+      __syncthreads();
+      // advance digit bases by this chunk's totals
+      { uint32_t tot = 0; for (int w = 0; w < SORT_THREADS / 32; w++) tot += warp_digit_cnt[w][tid]; digit_base[tid] += tot; }
+      __syncthreads();
+    }
+    uint64_t* t = src; src = dst; dst = t;
+    __syncthreads();
+  }
+  if (src != a) { for (int i = tid; i < n; i += SORT_THREADS) a[i] = src[i]; }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(SORT_THREADS)
+tile_sort_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ hdr, uint64_t* __restrict__ keys,
+                 uint64_t* __restrict__ keys_tmp, uint32_t* __restrict__ point_list) {
+  if (hdr[HDR_OVERFLOW]) return;
+  __shared__ uint64_t s[SORT_SMEM_KEYS];
+  const uint2 rg = ranges[blockIdx.x];
+  const int n = (int)(rg.y - rg.x);
+  if (n == 0) return;
+  uint64_t* bucket = keys + rg.x;
+  if (n <= SORT_SMEM_KEYS) {
+    int n2 = 1; while (n2 < n) n2 <<= 1;
+    for (int i = threadIdx.x; i < n2; i += SORT_THREADS) s[i] = (i < n) ? bucket[i] : ~0ull;
+    __syncthreads();
+    bitonic_smem(s, n2);
+    for (int i = threadIdx.x; i < n; i += SORT_THREADS) {
+      const uint64_t k = s[i];
+      bucket[i] = k;
+      point_list[rg.x + i] = (uint32_t)k;
+    }
+  } else {
+    radix_global(bucket, keys_tmp + rg.x, n);
+    for (int i = threadIdx.x; i < n; i += SORT_THREADS) point_list[rg.x + i] = (uint32_t)bucket[i];
+  }
+}
+
+}  // namespace
+
+void sfgs_launch_tile_scan(const ImageLayout& im, unsigned long long capacity, cudaStream_t st) {
+  SFGS_COUNT_LAUNCH();
+  tile_scan_kernel<<<1, SCAN_THREADS, 0, st>>>(im.tiles, im.tile_count, im.ranges, im.tile_cursor, im.hdr, capacity);
+}
+
+void sfgs_launch_emit(int P, const int* radii, const GeomLayout& g, const ImageLayout& im, const BinningLayout& b,
+                      cudaStream_t st) {
+  SFGS_COUNT_LAUNCH();
+  emit_keys_kernel<<<(P + 255) / 256, 256, 0, st>>>(P, radii, g.rec, im.tiles_x, im.tiles_y, im.ranges,
+                                                   im.tile_cursor, im.hdr, b.keys);
+}
+
+void sfgs_launch_tile_sort(const ImageLayout& im, const BinningLayout& b, cudaStream_t st) {
+  SFGS_COUNT_LAUNCH();
+  tile_sort_kernel<<<im.tiles, SORT_THREADS, 0, st>>>(im.ranges, im.hdr, b.keys, b.keys_tmp, b.point_list);
+}

@@ -1,0 +1,291 @@
+// sfgs_preprocess.cu — per-Gaussian projection stage (forward).
+//
+// Replaces FORWARD::preprocess / preprocessCUDA (RAST/cuda_rasterizer/forward.cu:214-328),
+// checkFrustum (RAST/cuda_rasterizer/rasterizer_impl.cu:54-66) and the
+// tile-instance counting that the reference obtains from its prefix sum
+// (rasterizer_impl.cu:283).  One thread per Gaussian; the result is one packed
+// 64-byte blend record per Gaussian plus a per-tile instance histogram.
+//
+// The arithmetic that decides tile/key indexing (view depth, projected centre,
+// 2D covariance, radius, tile rectangle) is written with the same operand
+// order and the same float/double promotions as the reference so that the
+// compiler contracts it into the same FMA sequence: radii, tiles_touched and
+// the depth bits of the sort key must be bit-identical.
+#include "sfgs_common.cuh"
+
+namespace {
+
+__device__ __forceinline__ float ndc_to_pix(float v, int S) {
+  // double arithmetic, as auxiliary.h:42-45 (its literals are doubles)
+  return ((v + 1.0) * S - 1.0) * 0.5;
+}
+
+struct Sym3 { float c0, c1, c2, c3, c4, c5; };
+
+// 3D covariance from scale * modifier and the (un-normalised) quaternion.
+// M = S * R (column-major glm semantics), Sigma = M^T M, upper triangle.
+// Mirrors computeCov3D, forward.cu:129-163.
+__device__ __forceinline__ void rot_from_quat(float r, float x, float y, float z, float R[3][3]) {
+  // R[c][k]: column c, row k, same element order as the glm::mat3 constructor call.
+  // The products below are pinned with explicit round-to-nearest intrinsics to the exact
+  // mul / fma split the reference's sm_100a binary uses for this block (read off its SASS:
+  // xy, yz and ry are fused into the add, rz, rx and xz are rounded products), because
+  // cov3D feeds the radius and therefore the tile/key indexing that must match bit for bit.
+  const float yy = __fmul_rn(y, y), zz = __fmul_rn(z, z);
+  const float rz = __fmul_rn(r, z), rx = __fmul_rn(r, x), xz = __fmul_rn(x, z);
+  const float s_yz = __fadd_rn(yy, zz);
+  const float s_xz = __fmaf_rn(x, x, zz);
+  const float s_xy = __fmaf_rn(x, x, yy);
+  const float xy_m_rz = __fmaf_rn(x, y, -rz), xy_p_rz = __fmaf_rn(x, y, rz);
+  const float xz_p_ry = __fmaf_rn(r, y, xz), xz_m_ry = __fmaf_rn(-r, y, xz);
+  const float yz_m_rx = __fmaf_rn(y, z, -rx), yz_p_rx = __fmaf_rn(y, z, rx);
+  R[0][0] = __fsub_rn(1.f, __fadd_rn(s_yz, s_yz)); R[0][1] = __fadd_rn(xy_m_rz, xy_m_rz); R[0][2] = __fadd_rn(xz_p_ry, xz_p_ry);
+  R[1][0] = __fadd_rn(xy_p_rz, xy_p_rz); R[1][1] = __fsub_rn(1.f, __fadd_rn(s_xz, s_xz)); R[1][2] = __fadd_rn(yz_m_rx, yz_m_rx);
+  R[2][0] = __fadd_rn(xz_m_ry, xz_m_ry); R[2][1] = __fadd_rn(yz_p_rx, yz_p_rx); R[2][2] = __fsub_rn(1.f, __fadd_rn(s_xy, s_xy));
+}
+
+__device__ __forceinline__ Sym3 cov3d_from_scale_rot(float sx, float sy, float sz, float mod,
+                                                     float qr, float qx, float qy, float qz) {
+  float R[3][3];
+  rot_from_quat(qr, qx, qy, qz, R);
+  const float s0 = mod * sx, s1 = mod * sy, s2 = mod * sz;
+  float M[3][3];
+#pragma unroll
+  for (int c = 0; c < 3; c++) { M[c][0] = s0 * R[c][0]; M[c][1] = s1 * R[c][1]; M[c][2] = s2 * R[c][2]; }
+  // Sigma[c][r] = M[r][0]*M[c][0] + M[r][1]*M[c][1] + M[r][2]*M[c][2]
+  Sym3 S;
+  S.c0 = M[0][0] * M[0][0] + M[0][1] * M[0][1] + M[0][2] * M[0][2];
+  S.c1 = M[1][0] * M[0][0] + M[1][1] * M[0][1] + M[1][2] * M[0][2];
+  S.c2 = M[2][0] * M[0][0] + M[2][1] * M[0][1] + M[2][2] * M[0][2];
+  S.c3 = M[1][0] * M[1][0] + M[1][1] * M[1][1] + M[1][2] * M[1][2];
+  S.c4 = M[2][0] * M[1][0] + M[2][1] * M[1][1] + M[2][2] * M[1][2];
+  S.c5 = M[2][0] * M[2][0] + M[2][1] * M[2][1] + M[2][2] * M[2][2];
+  return S;
+}
+
+// Shortest-axis normal, flipped toward the camera.  Mirrors computeNorm3D, forward.cu:167-211.
+__device__ __forceinline__ void normal_from_scale_rot(float sx, float sy, float sz,
+                                                      float qr, float qx, float qy, float qz,
+                                                      float px, float py, float pz,
+                                                      float cx, float cy, float cz, float n[3]) {
+  float R[3][3];
+  rot_from_quat(qr, qx, qy, qz, R);
+  float a0, a1, a2;
+  if (sx > sz && sy > sz) { a0 = 0.f; a1 = 0.f; a2 = 1.f; }
+  else if (sx > sy && sz > sy) { a0 = 0.f; a1 = 1.f; a2 = 0.f; }
+  else { a0 = 1.f; a1 = 0.f; a2 = 0.f; }
+  // transpose(R) * axis : out[r] = Rt[0][r]*a0 + Rt[1][r]*a1 + Rt[2][r]*a2, Rt[c][r] = R[r][c]
+  float n0 = R[0][0] * a0 + R[0][1] * a1 + R[0][2] * a2;
+  float n1 = R[1][0] * a0 + R[1][1] * a1 + R[1][2] * a2;
+  float n2 = R[2][0] * a0 + R[2][1] * a1 + R[2][2] * a2;
+  const float dx = px - cx, dy = py - cy, dz = pz - cz;
+  const float d = dx * n0 + dy * n1 + dz * n2;
+  if (d > 0) { n0 = -n0; n1 = -n1; n2 = -n2; }
+  n[0] = n0; n[1] = n1; n[2] = n2;
+}
+
+// EWA projection of the 3D covariance + Mip-Splatting 2D filter.
+// Mirrors computeCov2D, forward.cu:74-124. Returns (cov00+k, cov01, cov11+k, coef).
+__device__ __forceinline__ float4 cov2d_project(float mx, float my, float mz,
+                                                float focal_x, float focal_y,
+                                                float tan_fovx, float tan_fovy, float kernel_size,
+                                                const Sym3& V, const float* __restrict__ vm) {
+  float tx = vm[0] * mx + vm[4] * my + vm[8] * mz + vm[12];
+  float ty = vm[1] * mx + vm[5] * my + vm[9] * mz + vm[13];
+  const float tz = vm[2] * mx + vm[6] * my + vm[10] * mz + vm[14];
+  const float limx = 1.3f * tan_fovx;
+  const float limy = 1.3f * tan_fovy;
+  const float txtz = tx / tz;
+  const float tytz = ty / tz;
+  tx = min(limx, max(-limx, txtz)) * tz;
+  ty = min(limy, max(-limy, tytz)) * tz;
+
+  // J columns: (a0, 0, a2), (0, b1, b2), 0
+  const float a0 = focal_x / tz;
+  const float a2 = -(focal_x * tx) / (tz * tz);
+  const float b1 = focal_y / tz;
+  const float b2 = -(focal_y * ty) / (tz * tz);
+  // W columns: (vm0,vm4,vm8), (vm1,vm5,vm9), (vm2,vm6,vm10); T = W * J
+  float T0[3], T1[3];
+  T0[0] = vm[0] * a0 + vm[1] * 0.0f + vm[2] * a2;
+  T0[1] = vm[4] * a0 + vm[5] * 0.0f + vm[6] * a2;
+  T0[2] = vm[8] * a0 + vm[9] * 0.0f + vm[10] * a2;
+  T1[0] = vm[0] * 0.0f + vm[1] * b1 + vm[2] * b2;
+  T1[1] = vm[4] * 0.0f + vm[5] * b1 + vm[6] * b2;
+  T1[2] = vm[8] * 0.0f + vm[9] * b1 + vm[10] * b2;
+  // X = T^T * V^T : X[c][r] = T[r][0]*V[0][c] + T[r][1]*V[1][c] + T[r][2]*V[2][c]   (r = 0,1)
+  const float V0[3] = {V.c0, V.c1, V.c2}, V1[3] = {V.c1, V.c3, V.c4}, V2[3] = {V.c2, V.c4, V.c5};
+  float X0[3], X1[3];   // X0[c] = X[c][0], X1[c] = X[c][1]
+#pragma unroll
+  for (int c = 0; c < 3; c++) {
+    X0[c] = T0[0] * V0[c] + T0[1] * V1[c] + T0[2] * V2[c];
+    X1[c] = T1[0] * V0[c] + T1[1] * V1[c] + T1[2] * V2[c];
+  }
+  // cov[c][r] = X[0][r]*T[c][0] + X[1][r]*T[c][1] + X[2][r]*T[c][2]
+  float c00 = X0[0] * T0[0] + X0[1] * T0[1] + X0[2] * T0[2];
+  float c01 = X1[0] * T0[0] + X1[1] * T0[1] + X1[2] * T0[2];
+  float c11 = X1[0] * T1[0] + X1[1] * T1[1] + X1[2] * T1[2];
+
+  const float det_0 = fmax(1e-6, (double)(c00 * c11 - c01 * c01));
+  const float det_1 = fmax(1e-6, (double)((c00 + kernel_size) * (c11 + kernel_size) - c01 * c01));
+  float coef = sqrt(det_0 / (det_1 + 1e-6) + 1e-6);
+  if (det_0 <= 1e-6 || det_1 <= 1e-6) coef = 0.0f;
+  c00 += kernel_size;
+  c11 += kernel_size;
+  return make_float4(c00, c01, c11, coef);
+}
+
+// SH -> RGB (+0.5, clamp at 0 with mask). Mirrors computeColorFromSH, forward.cu:20-71.
+__device__ __forceinline__ void sh_to_rgb(int deg, const float* __restrict__ sh /* [M][3] */,
+                                          float px, float py, float pz, float cx, float cy, float cz,
+                                          float rgb[3], unsigned& clamp_mask) {
+  float dx = px - cx, dy = py - cy, dz = pz - cz;
+  const float len = sqrt(dx * dx + dy * dy + dz * dz);
+  dx = dx / len; dy = dy / len; dz = dz / len;
+  float res[3];
+#pragma unroll
+  for (int ch = 0; ch < 3; ch++) {
+    float r = SH_C0 * sh[0 * 3 + ch];
+    if (deg > 0) {
+      const float x = dx, y = dy, z = dz;
+      r = r - SH_C1 * y * sh[1 * 3 + ch] + SH_C1 * z * sh[2 * 3 + ch] - SH_C1 * x * sh[3 * 3 + ch];
+      if (deg > 1) {
+        const float xx = x * x, yy = y * y, zz = z * z;
+        const float xy = x * y, yz = y * z, xz = x * z;
+        r = r + SH_C2_0 * xy * sh[4 * 3 + ch] + SH_C2_1 * yz * sh[5 * 3 + ch] +
+            SH_C2_2 * (2.0f * zz - xx - yy) * sh[6 * 3 + ch] + SH_C2_3 * xz * sh[7 * 3 + ch] +
+            SH_C2_4 * (xx - yy) * sh[8 * 3 + ch];
+        if (deg > 2) {
+          r = r + SH_C3_0 * y * (3.0f * xx - yy) * sh[9 * 3 + ch] + SH_C3_1 * xy * z * sh[10 * 3 + ch] +
+              SH_C3_2 * y * (4.0f * zz - xx - yy) * sh[11 * 3 + ch] +
+              SH_C3_3 * z * (2.0f * zz - 3.0f * xx - 3.0f * yy) * sh[12 * 3 + ch] +
+              SH_C3_4 * x * (4.0f * zz - xx - yy) * sh[13 * 3 + ch] + SH_C3_5 * z * (xx - yy) * sh[14 * 3 + ch] +
+              SH_C3_6 * x * (xx - 3.0f * yy) * sh[15 * 3 + ch];
+        }
+      }
+    }
+    res[ch] = r + 0.5f;
+  }
+  clamp_mask = (res[0] < 0 ? 1u : 0u) | (res[1] < 0 ? 2u : 0u) | (res[2] < 0 ? 4u : 0u);
+  rgb[0] = fmaxf(res[0], 0.0f); rgb[1] = fmaxf(res[1], 0.0f); rgb[2] = fmaxf(res[2], 0.0f);
+}
+
+constexpr int PRE_THREADS = 256;
+
+__global__ void __launch_bounds__(PRE_THREADS)
+preprocess_kernel(int P, int D, int M,
+                  const float* __restrict__ means3D, const float* __restrict__ scales, float scale_modifier,
+                  const float* __restrict__ rotations, const float* __restrict__ opacities,
+                  const float* __restrict__ shs, const float* __restrict__ cov3D_precomp,
+                  const float* __restrict__ norm3D_precomp, const float* __restrict__ colors_precomp,
+                  const float* __restrict__ viewmatrix, const float* __restrict__ projmatrix,
+                  const float* __restrict__ cam_pos, int W, int H, float tan_fovx, float tan_fovy,
+                  float focal_x, float focal_y, float kernel_size, int gx, int gy,
+                  int* __restrict__ radii, float* __restrict__ rec, float* __restrict__ cov3D_out,
+                  unsigned char* __restrict__ clamped, uint32_t* __restrict__ tiles_touched,
+                  uint32_t* __restrict__ tile_count) {
+  const int idx = blockIdx.x * PRE_THREADS + threadIdx.x;
+  if (idx >= P) return;
+
+  const float px = means3D[3 * idx], py = means3D[3 * idx + 1], pz = means3D[3 * idx + 2];
+  const float* vm = viewmatrix;
+  const float* pm = projmatrix;
+
+  int out_radius = 0;
+  uint32_t out_tiles = 0;
+
+  const float view_z = vm[2] * px + vm[6] * py + vm[10] * pz + vm[14];
+  if (view_z > 0.2f) {
+    const float hx = pm[0] * px + pm[4] * py + pm[8] * pz + pm[12];
+    const float hy = pm[1] * px + pm[5] * py + pm[9] * pz + pm[13];
+    const float hw = pm[3] * px + pm[7] * py + pm[11] * pz + pm[15];
+    const float p_w = 1.0f / (hw + 0.0000001f);
+    const float proj_x = hx * p_w, proj_y = hy * p_w;
+
+    Sym3 V;
+    if (cov3D_precomp != nullptr) {
+      const float* c = cov3D_precomp + 6 * (size_t)idx;
+      V.c0 = c[0]; V.c1 = c[1]; V.c2 = c[2]; V.c3 = c[3]; V.c4 = c[4]; V.c5 = c[5];
+    } else {
+      const float sx = scales[3 * idx], sy = scales[3 * idx + 1], sz = scales[3 * idx + 2];
+      const float4 q = *reinterpret_cast<const float4*>(rotations + 4 * (size_t)idx);
+      V = cov3d_from_scale_rot(sx, sy, sz, scale_modifier, q.x, q.y, q.z, q.w);
+      float* co = cov3D_out + 6 * (size_t)idx;
+      co[0] = V.c0; co[1] = V.c1; co[2] = V.c2; co[3] = V.c3; co[4] = V.c4; co[5] = V.c5;
+    }
+
+    const float4 cov = cov2d_project(px, py, pz, focal_x, focal_y, tan_fovx, tan_fovy, kernel_size, V, vm);
+    const float det = (cov.x * cov.z - cov.y * cov.y);
+    if (det != 0.0f) {
+      const float det_inv = 1.f / det;
+      const float conx = cov.z * det_inv, cony = -cov.y * det_inv, conz = cov.x * det_inv;
+      const float mid = 0.5f * (cov.x + cov.z);
+      const float lambda1 = mid + sqrt(max(0.1f, mid * mid - det));
+      const float lambda2 = mid - sqrt(max(0.1f, mid * mid - det));
+      const float my_radius = ceil(3.f * sqrt(max(lambda1, lambda2)));
+      const float pix_x = ndc_to_pix(proj_x, W), pix_y = ndc_to_pix(proj_y, H);
+      const int iradius = my_radius;
+      const TileRect r = tile_rect(pix_x, pix_y, iradius, gx, gy);
+      const uint32_t ntiles = (uint32_t)((r.x1 - r.x0) * (r.y1 - r.y0));
+      if (ntiles != 0) {
+        float n[3];
+        if (norm3D_precomp != nullptr) {
+          n[0] = norm3D_precomp[3 * idx]; n[1] = norm3D_precomp[3 * idx + 1]; n[2] = norm3D_precomp[3 * idx + 2];
+        } else {
+          const float sx = scales[3 * idx], sy = scales[3 * idx + 1], sz = scales[3 * idx + 2];
+          const float4 q = *reinterpret_cast<const float4*>(rotations + 4 * (size_t)idx);
+          normal_from_scale_rot(sx, sy, sz, q.x, q.y, q.z, q.w, px, py, pz, cam_pos[0], cam_pos[1], cam_pos[2], n);
+        }
+        float rgb[3];
+        unsigned cmask = 0;
+        if (colors_precomp == nullptr) {
+          sh_to_rgb(D, shs + (size_t)idx * M * 3, px, py, pz, cam_pos[0], cam_pos[1], cam_pos[2], rgb, cmask);
+        } else {
+          rgb[0] = colors_precomp[3 * idx]; rgb[1] = colors_precomp[3 * idx + 1]; rgb[2] = colors_precomp[3 * idx + 2];
+        }
+        clamped[idx] = (unsigned char)cmask;
+
+        float4* o = reinterpret_cast<float4*>(rec + (size_t)idx * REC_FLOATS);
+        o[0] = make_float4(pix_x, pix_y, conx, cony);
+        o[1] = make_float4(conz, opacities[idx] * cov.w, view_z, 0.f);
+        o[2] = make_float4(rgb[0], rgb[1], rgb[2], n[0]);
+        o[3] = make_float4(n[1], n[2], 0.f, 0.f);
+        out_radius = iradius;
+        out_tiles = ntiles;
+        // per-tile instance histogram (replaces the per-Gaussian prefix sum of the reference)
+        for (int y = r.y0; y < r.y1; y++)
+          for (int x = r.x0; x < r.x1; x++) atomicAdd(&tile_count[y * gx + x], 1u);
+      }
+    }
+  }
+  radii[idx] = out_radius;
+  tiles_touched[idx] = out_tiles;
+}
+
+__global__ void mark_visible_kernel(int P, const float* __restrict__ means3D,
+                                    const float* __restrict__ vm, unsigned char* __restrict__ present) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= P) return;
+  const float px = means3D[3 * idx], py = means3D[3 * idx + 1], pz = means3D[3 * idx + 2];
+  const float view_z = vm[2] * px + vm[6] * py + vm[10] * pz + vm[14];
+  present[idx] = view_z > 0.2f ? 1 : 0;
+}
+
+}  // namespace
+
+void sfgs_launch_preprocess(const sfgs_forward_args* a, const GeomLayout& g, const ImageLayout& im,
+                            float focal_x, float focal_y, cudaStream_t st) {
+  const int blocks = (a->P + PRE_THREADS - 1) / PRE_THREADS;
+  SFGS_COUNT_LAUNCH();
+  preprocess_kernel<<<blocks, PRE_THREADS, 0, st>>>(
+      a->P, a->D, a->M, a->means3D, a->scales, a->scale_modifier, a->rotations, a->opacities, a->shs,
+      a->cov3D_precomp, a->norm3D_precomp, a->colors_precomp, a->viewmatrix, a->projmatrix, a->cam_pos,
+      a->width, a->height, a->tan_fovx, a->tan_fovy, focal_x, focal_y, a->kernel_size, im.tiles_x, im.tiles_y,
+      a->radii, g.rec, g.cov3D, g.clamped, g.tiles_touched, im.tile_count);
+}
+
+void sfgs_launch_mark_visible(int P, const float* means3D, const float* viewmatrix, unsigned char* present,
+                              cudaStream_t st) {
+  SFGS_COUNT_LAUNCH();
+  mark_visible_kernel<<<(P + 255) / 256, 256, 0, st>>>(P, means3D, viewmatrix, present);
+}

@@ -1,0 +1,148 @@
+// sfgs_render_fwd.cu — front-to-back alpha compositing, one CTA per 16x16 tile.
+//
+// Replaces FORWARD::render / renderCUDA (RAST/cuda_rasterizer/forward.cu:333-468).
+// Semantics kept exactly: pixel centres at integer coordinates, `power > 0`
+// skip, alpha = min(0.99, o*exp(power)), alpha < 1/255 skip, stop when
+// T*(1-alpha) < 1e-4 (that Gaussian is not applied), `contributor` counts every
+// tested entry, n_contrib = index of the last applied entry, colour gets
+// T*background, depth/normal/alpha have zero background.
+//
+// B200 mapping: each warp owns an 8x4 pixel block (coherent early-out); the
+// tile's sorted Gaussian list is streamed through a 2-stage cp.async ring of
+// packed 64-byte blend records, so the inner loop touches shared memory only
+// (the reference gathers colour/depth/normal from global memory per pixel).
+#include "sfgs_common.cuh"
+
+namespace {
+
+constexpr int FWD_THREADS = 256;
+constexpr int FWD_BATCH = 128;   // records per stage
+constexpr int FWD_STAGES = 2;
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+template <bool HAS_EXTRA>
+__global__ void __launch_bounds__(FWD_THREADS)
+render_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list,
+                  const uint32_t* __restrict__ hdr, int W, int H, int ED,
+                  const float* __restrict__ rec, const float* __restrict__ extras,
+                  const float* __restrict__ bg_color, float* __restrict__ out_color,
+                  float* __restrict__ out_depth, float* __restrict__ out_norm, float* __restrict__ out_alpha,
+                  float* __restrict__ out_extra, uint32_t* __restrict__ n_contrib) {
+  if (hdr[HDR_OVERFLOW]) return;
+  __shared__ __align__(16) float4 s_rec[FWD_STAGES][FWD_BATCH][4];   // 16 KB
+  __shared__ uint32_t s_id[FWD_STAGES][FWD_BATCH];
+
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int tiles_x = (W + SFGS_TILE - 1) / SFGS_TILE;
+  const int tile = blockIdx.y * tiles_x + blockIdx.x;
+  // warp w covers the 8x4 block (w%2, w/2) of the tile, lane -> (lane%8, lane/8)
+  const int px = blockIdx.x * SFGS_TILE + (wid & 1) * 8 + (lane & 7);
+  const int py = blockIdx.y * SFGS_TILE + (wid >> 1) * 4 + (lane >> 3);
+  const bool inside = px < W && py < H;
+  const uint32_t pix_id = (uint32_t)W * py + px;
+  const float pixfx = (float)px, pixfy = (float)py;
+
+  const uint2 range = ranges[tile];
+  const int total = (int)(range.y - range.x);
+  const int nbatches = (total + FWD_BATCH - 1) / FWD_BATCH;
+
+  float T = 1.0f;
+  uint32_t contributor = 0, last_contributor = 0;
+  float C0 = 0.f, C1 = 0.f, C2 = 0.f, Dp = 0.f, N0 = 0.f, N1 = 0.f, N2 = 0.f;
+  float E[HAS_EXTRA ? SFGS_MAX_EXTRA : 1];
+  if (HAS_EXTRA) {
+#pragma unroll
+    for (int i = 0; i < SFGS_MAX_EXTRA; i++) E[i] = 0.f;
+  }
+  bool done = !inside;
+
+  // stage loader: thread t (< FWD_BATCH*... ) copies quarter q of record e
+  auto issue = [&](int batch, int stage) {
+    const int base = batch * FWD_BATCH;
+    // 128 records x 4 quarters = 512 16-byte copies over 256 threads
+#pragma unroll
+    for (int k = 0; k < (FWD_BATCH * 4) / FWD_THREADS; k++) {
+      const int c = tid + k * FWD_THREADS;
+      const int e = c >> 2, q = c & 3;
+      if (base + e < total) {
+        const uint32_t id = point_list[range.x + base + e];
+        cp_async16(&s_rec[stage][e][q], rec + (size_t)id * REC_FLOATS + q * 4);
+        if (q == 0) s_id[stage][e] = id;
+      }
+    }
+    cp_async_commit();
+  };
+
+  if (nbatches > 0) issue(0, 0);
+  for (int b = 0; b < nbatches; b++) {
+    const int stage = b & 1;
+    cp_async_wait<0>();
+    // barrier: stage `b` visible to all, stage `b^1` no longer read by anyone
+    const int num_done = __syncthreads_count(done);
+    if (num_done == FWD_THREADS) break;
+    if (b + 1 < nbatches) issue(b + 1, stage ^ 1);
+    const int cnt = min(FWD_BATCH, total - b * FWD_BATCH);
+    for (int j = 0; !done && j < cnt; j++) {
+      contributor = (uint32_t)(b * FWD_BATCH + j + 1);
+      const float4 a = s_rec[stage][j][0];   // mx, my, con.x, con.y
+      const float4 c = s_rec[stage][j][1];   // con.z, opac, depth, -
+      const float dx = a.x - pixfx, dy = a.y - pixfy;
+      const float power = -0.5f * (a.z * dx * dx + c.x * dy * dy) - a.w * dx * dy;
+      if (power > 0.0f) continue;
+      const float alpha = min(0.99f, c.y * exp(power));
+      if (alpha < 1.0f / 255.0f) continue;
+      const float test_T = T * (1 - alpha);
+      if (test_T < 0.0001f) { done = true; continue; }
+      const float4 f = s_rec[stage][j][2];   // r, g, b, nx
+      const float4 g = s_rec[stage][j][3];   // ny, nz
+      C0 += f.x * alpha * T; C1 += f.y * alpha * T; C2 += f.z * alpha * T;
+      Dp += c.z * alpha * T;
+      N0 += f.w * alpha * T; N1 += g.x * alpha * T; N2 += g.y * alpha * T;
+      if (HAS_EXTRA) {
+        const float* ex = extras + (size_t)s_id[stage][j] * ED;
+        for (int ch = 0; ch < ED; ch++) E[ch] += ex[ch] * alpha * T;
+      }
+      T = test_T;
+      last_contributor = contributor;
+    }
+  }
+
+  if (inside) {
+    const size_t HW = (size_t)H * W;
+    out_alpha[pix_id] = 1 - T;
+    n_contrib[pix_id] = last_contributor;
+    out_color[0 * HW + pix_id] = C0 + T * bg_color[0];
+    out_color[1 * HW + pix_id] = C1 + T * bg_color[1];
+    out_color[2 * HW + pix_id] = C2 + T * bg_color[2];
+    out_depth[pix_id] = Dp;
+    out_norm[0 * HW + pix_id] = N0;
+    out_norm[1 * HW + pix_id] = N1;
+    out_norm[2 * HW + pix_id] = N2;
+    if (HAS_EXTRA)
+      for (int ch = 0; ch < ED; ch++) out_extra[ch * HW + pix_id] = E[ch];
+  }
+}
+
+}  // namespace
+
+void sfgs_launch_render_fwd(const sfgs_forward_args* a, const GeomLayout& g, const ImageLayout& im,
+                            const BinningLayout& b, cudaStream_t st) {
+  dim3 grid(im.tiles_x, im.tiles_y, 1);
+  SFGS_COUNT_LAUNCH();
+  if (a->ED > 0)
+    render_fwd_kernel<true><<<grid, FWD_THREADS, 0, st>>>(im.ranges, b.point_list, im.hdr, a->width, a->height, a->ED,
+                                                         g.rec, a->extra_attrs, a->background, a->out_color,
+                                                         a->out_depth, a->out_norm, a->out_alpha, a->out_extra,
+                                                         im.n_contrib);
+  else
+    render_fwd_kernel<false><<<grid, FWD_THREADS, 0, st>>>(im.ranges, b.point_list, im.hdr, a->width, a->height, 0,
+                                                          g.rec, nullptr, a->background, a->out_color, a->out_depth,
+                                                          a->out_norm, a->out_alpha, nullptr, im.n_contrib);
+}
