@@ -1,0 +1,433 @@
+#!/usr/bin/env python
+"""bench.py — rasterizer fwd+bwd Mpix/s @1080p (1M Gaussians) on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+One "step" = one forward + one backward of the splat rasterizer over the
+BASELINE.json configs[1] workload on synthetic data: the JAX_004-shaped scene of
+sfgs.synthetic.city_scene (1M Gaussians, SH degree 3) seen by frame 0 of the
+reference's JAX_004 camera path at 1920x1080, with fixed N(0,1) pixel cotangents.
+
+Printed (rank 0, ONE JSON line):
+  value    fwd+bwd Mpix/s through the C ABI (ctypes, same call the diff_gauss._C
+           stand-in makes) with every input resident in HBM; per-step CUDA events
+           on the launching stream, L2 flushed between steps, max over ranks.
+  e2e      the same metric through the public autograd API (diff_gauss.GaussianRasterizer
+           -> loss -> backward); per step the camera matrices and the target image are
+           copied host->device from pinned memory and the loss is read back.
+  roofline the dominant kernel: algorithmic bytes per launch (SURVEY.md §8d / DESIGN.md)
+           / its mean launch duration measured live with CUDA events around the launch.
+  cpu_baseline  the CPU oracle (oracle/sfgs_oracle.c, a port: the reference has no CPU
+           path) timed on this box's host cores on a bounded sample.
+`--impl reference` times the UNMODIFIED reference CUDA rasterizer (oracle/_ref, built from
+/root/reference's own sources) the same two ways; if that library is absent it falls back
+to the CPU oracle port.  Multi-GPU: ranks render different cameras of the replicated scene
+(weak scaling, no data-path collective); `--shard tilerows` splits ONE frame by tile rows
+and all-gathers the image with NCCL (strong scaling, BASELINE configs[3] style).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "skyfall-gs_b200")
+for p in (ROOT, PKG):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+from sfgs import synthetic as S  # noqa: E402
+
+W_IMG, H_IMG = 1920, 1080
+P_GAUSS = 1_000_000
+SH_DEGREE = 3
+METRIC = "rasterizer fwd+bwd Mpix/s @1080p (1M Gaussians)"
+
+
+# ----------------------------------------------------------------------------- helpers
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+
+    def __init__(self, index: int):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def camera_for_rank(rank: int, world: int) -> S.Camera:
+    """Rank 0 sees the JAX_004 frame-0 camera; other ranks the same orbit rotated about the scene's z axis."""
+    if rank == 0:
+        return S.jax004_camera(W_IMG, H_IMG)
+    ang = 2.0 * math.pi * rank / max(world, 1)
+    rot = np.array([[math.cos(ang), -math.sin(ang), 0, 0], [math.sin(ang), math.cos(ang), 0, 0], [0, 0, 1, 0], [0, 0, 0, 1.0]])
+    return S.camera_from_c2w_opengl(rot @ S.JAX004_FRAME0_C2W, S.JAX004_FOV_DEG, W_IMG, H_IMG)
+
+
+def algorithmic_bytes(P, V, R, N, M, tiles):
+    """SURVEY.md §8d compulsory traffic, split by stage (each input read once, each output written once)."""
+    return {
+        "preprocess": 20 * P + (111 + 12 * M) * V,
+        "tile_scan": 8 * tiles + 8 * P,
+        "emit_keys": 20 * V + 12 * R,
+        "tile_sort": 32 * R,
+        "render_fwd": 56 * R + 36 * N + 8 * tiles,
+        "render_bwd": 56 * R + 40 * N + 120 * V,
+        "gauss_bwd": (124 + 12 * M) * P + (291 + 24 * M) * V,
+    }
+
+
+class L2Flusher:
+    def __init__(self, dev):
+        self.buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
+
+    def __call__(self):
+        self.buf.add_(1)
+
+
+# ----------------------------------------------------------------------------- device-resident leg ("value")
+def make_inputs(scene, cam, dev):
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)  # noqa: E731
+    d = dict(means3D=t(scene.means3D), scales=t(scene.scales), rotations=t(scene.rotations),
+             opacities=t(scene.opacities), shs=t(scene.shs), viewmatrix=t(cam.viewmatrix),
+             projmatrix=t(cam.projmatrix), campos=t(cam.campos), bg=torch.zeros(3, device=dev))
+    d["cot"] = [t(c) for c in S.cotangents(cam.width, cam.height, seed=1)]
+    d["empty"] = torch.empty(0, device=dev)
+    return d
+
+
+def step_ours(d, cam):
+    from sfgs import rasterizer as R
+    e = d["empty"]
+    f = R.rasterize_gaussians(d["bg"], d["means3D"], e, d["opacities"], d["scales"], d["rotations"], 1.0, e, e, e, 0,
+                              d["viewmatrix"], d["projmatrix"], cam.tanfovx, cam.tanfovy, 0.1, cam.height, cam.width,
+                              d["shs"], SH_DEGREE, d["campos"], False, False)
+    c = d["cot"]
+    g = R.rasterize_gaussians_backward(d["bg"], d["means3D"], f[5], e, d["scales"], d["rotations"], e, 1.0, e, e,
+                                       d["viewmatrix"], d["projmatrix"], cam.tanfovx, cam.tanfovy, 0.1, c[0], c[1],
+                                       c[2], c[3], e, d["shs"], SH_DEGREE, d["campos"], f[7], f[0], f[8], f[9], f[4],
+                                       False)
+    return f, g
+
+
+def step_ref(d, cam):
+    from oracle import ref_cuda
+    e = d["empty"]
+    f = ref_cuda.forward(d["bg"], d["means3D"], e, d["opacities"], d["scales"], d["rotations"], 1.0, e, e, e,
+                         d["viewmatrix"], d["projmatrix"], cam.tanfovx, cam.tanfovy, 0.1, cam.height, cam.width,
+                         d["shs"], SH_DEGREE, d["campos"])
+    c = d["cot"]
+    g = ref_cuda.backward(d["bg"], d["means3D"], f["radii"], e, d["scales"], d["rotations"], e, 1.0, e, e,
+                          d["viewmatrix"], d["projmatrix"], cam.tanfovx, cam.tanfovy, 0.1, c[0], c[1], c[2], c[3], e,
+                          d["shs"], SH_DEGREE, d["campos"], f["geom"], f["num_rendered"], f["binning"], f["img"],
+                          f["alpha"])
+    return f, g
+
+
+def timed_steps(step_fn, steps, warmup, flush, dev):
+    for _ in range(warmup):
+        step_fn()
+    torch.cuda.synchronize(dev)
+    evs = []
+    for _ in range(steps):
+        flush()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        step_fn()
+        b.record()
+        evs.append((a, b))
+    torch.cuda.synchronize(dev)
+    return [a.elapsed_time(b) for a, b in evs]   # ms per step
+
+
+# ----------------------------------------------------------------------------- public-API leg ("e2e")
+class E2EOurs:
+    """render -> L1-style loss -> backward through diff_gauss, with per-step H2D of camera + target image."""
+
+    def __init__(self, scene, cam, dev):
+        from diff_gauss import GaussianRasterizationSettings, GaussianRasterizer
+        self.GRS, self.GR = GaussianRasterizationSettings, GaussianRasterizer
+        t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)  # noqa: E731
+        self.dev, self.cam = dev, cam
+        self.params = [t(scene.means3D).requires_grad_(True), t(scene.opacities).requires_grad_(True),
+                       t(scene.shs).requires_grad_(True), t(scene.scales).requires_grad_(True),
+                       t(scene.rotations).requires_grad_(True)]
+        self.means2D = torch.zeros((scene.P, 3), device=dev, requires_grad=True)
+        rng = np.random.default_rng(5)
+        self.h_cam = torch.from_numpy(np.concatenate([cam.viewmatrix.ravel(), cam.projmatrix.ravel(), cam.campos])).pin_memory()
+        self.h_gt = torch.from_numpy(rng.uniform(0, 1, size=(3, cam.height, cam.width)).astype(np.float32)).pin_memory()
+        self.h_loss = torch.zeros(1).pin_memory()
+        self.bg = torch.zeros(3, device=dev)
+        self.sub = torch.zeros(1, device=dev)
+        self.h2d_bytes = self.h_cam.numel() * 4 + self.h_gt.numel() * 4
+        self.d2h_bytes = 4
+
+    def step(self):
+        cam = self.cam
+        dcam = self.h_cam.to(self.dev, non_blocking=True)
+        gt = self.h_gt.to(self.dev, non_blocking=True)
+        rs = self.GRS(cam.height, cam.width, cam.tanfovx, cam.tanfovy, 0.1, self.sub, self.bg, 1.0,
+                      dcam[0:16].view(4, 4), dcam[16:32].view(4, 4), SH_DEGREE, dcam[32:35], False, False)
+        means3D, opac, shs, scales, rots = self.params
+        color, depth, norm, alpha, radii, _ = self.GR(rs)(means3D, self.means2D, opac, shs=shs, scales=scales,
+                                                          rotations=rots)
+        loss = (color - gt).abs().mean() + 0.01 * depth.mean() + 0.01 * (1 - alpha).mean() + 0.01 * norm.mean()
+        for p in self.params:
+            p.grad = None
+        self.means2D.grad = None
+        loss.backward()
+        self.h_loss.copy_(loss.detach().reshape(1), non_blocking=True)
+
+
+class E2ERef:
+    """The same step through the unmodified reference CUDA rasterizer (no autograd wrapper: gradients of the
+    same loss are formed by hand and fed to its backward)."""
+
+    def __init__(self, scene, cam, dev):
+        self.d = make_inputs(scene, cam, dev)
+        self.dev, self.cam = dev, cam
+        rng = np.random.default_rng(5)
+        self.h_cam = torch.from_numpy(np.concatenate([cam.viewmatrix.ravel(), cam.projmatrix.ravel(), cam.campos])).pin_memory()
+        self.h_gt = torch.from_numpy(rng.uniform(0, 1, size=(3, cam.height, cam.width)).astype(np.float32)).pin_memory()
+        self.h_loss = torch.zeros(1).pin_memory()
+        self.h2d_bytes = self.h_cam.numel() * 4 + self.h_gt.numel() * 4
+        self.d2h_bytes = 4
+
+    def step(self):
+        from oracle import ref_cuda
+        d, cam, e = self.d, self.cam, self.d["empty"]
+        dcam = self.h_cam.to(self.dev, non_blocking=True)
+        gt = self.h_gt.to(self.dev, non_blocking=True)
+        view, proj, campos = dcam[0:16].view(4, 4), dcam[16:32].view(4, 4), dcam[32:35]
+        f = ref_cuda.forward(d["bg"], d["means3D"], e, d["opacities"], d["scales"], d["rotations"], 1.0, e, e, e, view,
+                             proj, cam.tanfovx, cam.tanfovy, 0.1, cam.height, cam.width, d["shs"], SH_DEGREE, campos)
+        n = float(cam.height * cam.width)
+        norm_raw = f["norm"].detach().requires_grad_(True)
+        norm = torch.nn.functional.normalize(norm_raw, p=2, dim=0)
+        loss = (f["color"] - gt).abs().mean() + 0.01 * f["depth"].mean() + 0.01 * (1 - f["alpha"]).mean() + 0.01 * norm.mean()
+        (g_norm,) = torch.autograd.grad(0.01 * norm.mean(), norm_raw)
+        g_color = torch.sign(f["color"] - gt) / (3 * n)
+        g_depth = torch.full_like(f["depth"], 0.01 / n)
+        g_alpha = torch.full_like(f["alpha"], -0.01 / n)
+        ref_cuda.backward(d["bg"], d["means3D"], f["radii"], e, d["scales"], d["rotations"], e, 1.0, e, e, view, proj,
+                          cam.tanfovx, cam.tanfovy, 0.1, g_color, g_depth, g_norm, g_alpha, e, d["shs"], SH_DEGREE,
+                          campos, f["geom"], f["num_rendered"], f["binning"], f["img"], f["alpha"])
+        self.h_loss.copy_(loss.detach().reshape(1), non_blocking=True)
+
+
+# ----------------------------------------------------------------------------- CPU baseline
+def cpu_baseline(scene, cam, max_seconds=25.0):
+    """CPU oracle (port of the reference algorithm; the reference itself has no CPU path) on this box's cores."""
+    from oracle import cpu_oracle as O
+    cot = S.cotangents(cam.width, cam.height, seed=1)
+    bg = np.zeros(3, np.float32)
+    times = []
+    t_start = time.perf_counter()
+    while True:
+        t0 = time.perf_counter()
+        f = O.forward(scene.means3D, scene.scales, scene.rotations, scene.opacities, scene.shs, scene.sh_degree,
+                      cam.viewmatrix, cam.projmatrix, cam.campos, cam.width, cam.height, cam.tanfovx, cam.tanfovy, bg)
+        O.backward(f, *cot)
+        times.append(time.perf_counter() - t0)
+        if time.perf_counter() - t_start > max_seconds * 0.6 or len(times) >= 4:
+            break
+    best = min(times)
+    return {"value": cam.width * cam.height / best / 1e6, "unit": "Mpix/s", "cores": O.num_threads(), "kind": "port",
+            "sample": f"{len(times)} full fwd+bwd step(s) of the same workload (P={scene.P}, {cam.width}x{cam.height}), "
+                      f"best of {len(times)}, OpenMP over {O.num_threads()} threads"}
+
+
+# ----------------------------------------------------------------------------- main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--shard", default="views", choices=["views", "tilerows"])
+    ap.add_argument("--P", type=int, default=P_GAUSS)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    steps, warmup = max(1, args.steps), max(3, args.warmup)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+    dev = torch.device(f"cuda:{local_rank}")
+    torch.cuda.set_device(dev)
+
+    from oracle import ref_cuda
+    use_ref_cuda = args.impl == "reference" and ref_cuda.available()
+    if args.impl == "reference" and not use_ref_cuda:
+        return reference_cpu_arm(args, rank, world, steps, warmup)
+
+    if args.shard == "tilerows" and world > 1 and args.impl == "ours":
+        from sfgs import multigpu
+        return multigpu.bench_tilerows(args, rank, world, dev, steps, warmup, METRIC)
+
+    scene = S.city_scene(args.P, seed=0, sh_degree=SH_DEGREE)
+    cam = camera_for_rank(rank, world)
+    N = cam.width * cam.height
+    d = make_inputs(scene, cam, dev)
+    flush = L2Flusher(dev)
+
+    from sfgs import native
+    if args.impl == "ours":
+        native.lib()
+        step = lambda: step_ours(d, cam)  # noqa: E731
+    else:
+        step = lambda: step_ref(d, cam)   # noqa: E731
+
+    # ---- value: device-resident inputs, per-step events, max over ranks
+    sampler = ClockSampler(local_rank)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    launches0 = native.lib().sfgs_launch_count() if args.impl == "ours" else 0
+    sampler.start()
+    ms = timed_steps(step, steps, warmup, flush, dev)
+    clocks = sampler.stop()
+    launches = (native.lib().sfgs_launch_count() - launches0) if args.impl == "ours" else None
+    total_ms = torch.tensor([sum(ms)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.barrier()
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    total_ms = float(total_ms.item())
+    value = world * steps * N / (total_ms / 1e3) / 1e6
+
+    # ---- e2e: public API with host<->device copies inside the timed region
+    e2e_obj = (E2EOurs if args.impl == "ours" else E2ERef)(scene, cam, dev)
+    e2e_ms = timed_steps(e2e_obj.step, steps, warmup, flush, dev)
+    e2e_total = torch.tensor([sum(e2e_ms)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_total, op=dist.ReduceOp.MAX)
+    e2e_value = world * steps * N / (float(e2e_total.item()) / 1e3) / 1e6
+    del e2e_obj
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- stage profile + roofline (rank 0, ours only)
+    out = {"metric": METRIC, "value": round(value, 2), "unit": "Mpix/s", "n_gpus": world, "steps": steps,
+           "warmup": warmup, "ms_per_step": round(total_ms / steps, 4), "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": "BASELINE configs[1]: JAX_004-shaped synthetic scene, 1M Gaussians, SH degree 3, "
+                                  "1920x1080, JAX_004 frame-0 camera, fwd+bwd, fixed N(0,1) cotangents",
+                      "P": scene.P, "width": cam.width, "height": cam.height, "sh_degree": SH_DEGREE,
+                      "parallelism": f"views x{world} (one camera per GPU, scene replicated, no collective)",
+                      "l2": "flushed between steps (256 MB write)", "timing": "per-step CUDA events, max over ranks"},
+           "e2e": {"value": round(e2e_value, 2), "unit": "Mpix/s", "h2d_bytes_per_step": (16 + 16 + 3) * 4 + 3 * N * 4,
+                   "d2h_bytes_per_step": 4},
+           "clocks": clocks}
+    out["e2e"]["api"] = ("diff_gauss.GaussianRasterizer + autograd" if args.impl == "ours"
+                         else "reference CudaRasterizer::Rasterizer forward/backward")
+    if args.impl == "ours":
+        out["gpu_launches"] = int(launches)
+        f, _ = step()
+        torch.cuda.synchronize(dev)
+        R, V = int(f[0]), int((f[5] > 0).sum().item())
+        M = (SH_DEGREE + 1) ** 2
+        tiles = ((cam.width + 15) // 16) * ((cam.height + 15) // 16)
+        native.profile_enable(True)
+        for _ in range(steps):
+            flush()
+            step()
+        torch.cuda.synchronize(dev)
+        prof = native.profile_read()
+        native.profile_enable(False)
+        alg = algorithmic_bytes(scene.P, V, R, N, M, tiles)
+        stage_ms = {k: (v[0] / v[1] if v[1] else 0.0) for k, v in prof.items()}
+        dom = max((k for k in stage_ms if k in alg), key=lambda k: stage_ms[k])
+        peak, peak_src = peaks()
+        ach = alg[dom] / (stage_ms[dom] / 1e3) / 1e9
+        b_total = sum(alg.values())
+        t_kernels = sum(stage_ms.values())
+        out["roofline"] = {"bound": "hbm", "kernel": dom, "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
+                           "frac": round(ach / peak, 4), "traffic": None, "peak_source": peak_src,
+                           "algorithmic_bytes": int(alg[dom]), "kernel_ms": round(stage_ms[dom], 4),
+                           "share_of_step": round(stage_ms[dom] / t_kernels, 3)}
+        out["roofline_pipeline"] = {"algorithmic_bytes": int(b_total), "kernels_ms": round(t_kernels, 4),
+                                    "achieved": round(b_total / (t_kernels / 1e3) / 1e9, 1), "unit": "GB/s",
+                                    "frac": round(b_total / (t_kernels / 1e3) / 1e9 / peak, 4)}
+        out["stages_ms"] = {k: round(v, 4) for k, v in stage_ms.items()}
+        out["counts"] = {"P": scene.P, "V": V, "R": R, "N": N}
+    else:
+        out["impl"] = "reference"
+        out["reference_kind"] = "unmodified reference CUDA rasterizer (oracle/_ref), same GPU, same inputs"
+        out["e2e"]["note"] = "same host<->device copies as the product arm"
+    if not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_baseline(scene, cam)
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def reference_cpu_arm(args, rank, world, steps, warmup):
+    """Fallback reference arm when oracle/_ref is absent: the CPU oracle port on the host cores (rank 0 only)."""
+    if rank != 0:
+        return
+    scene = S.city_scene(args.P, seed=0, sh_degree=SH_DEGREE)
+    cam = S.jax004_camera(W_IMG, H_IMG)
+    cb = cpu_baseline(scene, cam, max_seconds=60.0)
+    out = {"metric": METRIC, "value": round(cb["value"], 4), "unit": "Mpix/s", "n_gpus": world, "steps": steps,
+           "warmup": warmup, "ms_per_step": round(cam.width * cam.height / cb["value"] / 1e3, 2),
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "impl": "reference", "config": {"workload": "BASELINE configs[1] (same as the product arm)"},
+           "cpu_baseline": cb,
+           "e2e": {"value": round(cb["value"], 4), "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()

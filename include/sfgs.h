@@ -195,8 +195,20 @@ int sfgs_fusedssim_backward(float C1, float C2, int B, int CH, int H, int W,
 int sfgs_dist2_knn3(int P, const float* points, float* mean_dist2,
                     sfgs_alloc_fn scratch_alloc, void* scratch_user, void* stream);
 
+/* ---- optional per-stage device timing ---------------------------------------- */
+/* Stage order: 0 fwd zero-fill, 1 preprocess, 2 tile scan, 3 key emission, 4 tile sort, 5 blend fwd,
+ * 6 bwd zero-fill, 7 blend bwd, 8 per-Gaussian bwd.  When enabled, every stage is bracketed by CUDA events
+ * on the caller's stream; sfgs_profile_read() synchronises those events and returns accumulated
+ * milliseconds and launch counts per stage (returns the number of stages).  Off by default. */
+#define SFGS_NUM_STAGES 9
+int sfgs_profile_enable(int on);
+int sfgs_profile_read(double* ms_total, long long* launches, int n);
+
 /* ---- misc ---------------------------------------------------------------- */
 const char* sfgs_last_error(void);
+/* sizeof() of the ABI structs as compiled (0 forward_args, 1 backward_args, 2 geom_view, 3 image_view,
+ * 4 binning_view) so that foreign-language bindings can verify their mirror definitions */
+size_t sfgs_sizeof(int which);
 int sfgs_version(void);
 /* number of kernel launches issued by this library since load (for bench.py's gpu_launches) */
 long long sfgs_launch_count(void);

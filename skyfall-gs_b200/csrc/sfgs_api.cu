@@ -13,6 +13,7 @@
 #include <cstring>
 #include <atomic>
 #include <mutex>
+#include <vector>
 #include "sfgs_common.cuh"
 
 long long g_sfgs_launches = 0;
@@ -24,7 +25,7 @@ void sfgs_launch_mark_visible(int P, const float* means3D, const float* viewmatr
 void sfgs_launch_tile_scan(const ImageLayout& im, unsigned long long capacity, cudaStream_t st);
 void sfgs_launch_emit(int P, const int* radii, const GeomLayout& g, const ImageLayout& im, const BinningLayout& b,
                       cudaStream_t st);
-void sfgs_launch_tile_sort(const ImageLayout& im, const BinningLayout& b, cudaStream_t st);
+void sfgs_launch_tile_sort(const GeomLayout& g, const ImageLayout& im, const BinningLayout& b, cudaStream_t st);
 void sfgs_launch_render_fwd(const sfgs_forward_args* a, const GeomLayout& g, const ImageLayout& im,
                             const BinningLayout& b, cudaStream_t st);
 void sfgs_launch_render_bwd(const sfgs_backward_args* a, const GeomLayout& g, const ImageLayout& im,
@@ -59,6 +60,43 @@ int fail(int code, const char* what, cudaError_t e = cudaSuccess) {
       if (_e != cudaSuccess) return fail(SFGS_E_CUDA, "stage " name, _e);              \
     }                                                                                  \
   } while (0)
+
+// ---- optional per-stage device timing (bench.py's roofline uses it; off by default) ----
+enum { ST_FWD_ZERO = 0, ST_PREPROCESS, ST_SCAN, ST_EMIT, ST_SORT, ST_RENDER_FWD, ST_BWD_ZERO, ST_RENDER_BWD, ST_GAUSS_BWD, ST_COUNT };
+struct StageProf {
+  bool on = false;
+  struct Span { cudaEvent_t a, b; int stage; };
+  std::vector<Span> spans;
+  std::vector<Span> pool;
+  double ms[ST_COUNT] = {0};
+  long long n[ST_COUNT] = {0};
+  cudaEvent_t cur_a = nullptr, cur_b = nullptr;
+  void begin(int stage, cudaStream_t st) {
+    if (!on) return;
+    Span s;
+    if (!pool.empty()) { s = pool.back(); pool.pop_back(); }
+    else { cudaEventCreate(&s.a); cudaEventCreate(&s.b); }
+    s.stage = stage;
+    cudaEventRecord(s.a, st);
+    spans.push_back(s);
+  }
+  void end(cudaStream_t st) {
+    if (!on || spans.empty()) return;
+    cudaEventRecord(spans.back().b, st);
+  }
+  void collect() {
+    for (auto& s : spans) {
+      float t = 0.f;
+      if (cudaEventSynchronize(s.b) == cudaSuccess && cudaEventElapsedTime(&t, s.a, s.b) == cudaSuccess) { ms[s.stage] += t; n[s.stage]++; }
+      pool.push_back(s);
+    }
+    spans.clear();
+  }
+};
+StageProf g_prof;
+std::mutex g_prof_mu;
+#define PROF_BEGIN(stage) g_prof.begin(stage, st)
+#define PROF_END() g_prof.end(st)
 
 struct PinnedHdr {
   uint32_t* p = nullptr;
@@ -137,11 +175,15 @@ int sfgs_rasterize_forward(const sfgs_forward_args* a) {
   ImageLayout im(sfgs_align_ptr(iptr), a->width, a->height);
 
   // tile histogram + header start at zero
+  PROF_BEGIN(ST_FWD_ZERO);
   CU(cudaMemsetAsync(im.hdr, 0, IMG_HDR_WORDS * sizeof(uint32_t), st));
   CU(cudaMemsetAsync(im.tile_count, 0, (size_t)im.tiles * sizeof(uint32_t), st));
+  PROF_END();
 
   if (P > 0) {
+    PROF_BEGIN(ST_PREPROCESS);
     sfgs_launch_preprocess(a, g, im, focal_x, focal_y, st);
+    PROF_END();
     STAGE_CHECK("preprocess");
   }
 
@@ -160,15 +202,23 @@ int sfgs_rasterize_forward(const sfgs_forward_args* a) {
     if (!bptr) return fail(SFGS_E_ALLOC, "forward: binning allocator returned NULL");
     BinningLayout b(sfgs_align_ptr(bptr), (size_t)capacity);
 
+    PROF_BEGIN(ST_SCAN);
     sfgs_launch_tile_scan(im, (unsigned long long)capacity, st);
+    PROF_END();
     STAGE_CHECK("tile_scan");
     if (P > 0) {
+      PROF_BEGIN(ST_EMIT);
       sfgs_launch_emit(P, a->radii, g, im, b, st);
+      PROF_END();
       STAGE_CHECK("emit_keys");
-      sfgs_launch_tile_sort(im, b, st);
+      PROF_BEGIN(ST_SORT);
+      sfgs_launch_tile_sort(g, im, b, st);
+      PROF_END();
       STAGE_CHECK("tile_sort");
     }
+    PROF_BEGIN(ST_RENDER_FWD);
     sfgs_launch_render_fwd(a, g, im, b, st);
+    PROF_END();
     STAGE_CHECK("render_fwd");
 
     CU(cudaMemcpyAsync(hhdr, im.hdr, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
@@ -212,16 +262,48 @@ int sfgs_rasterize_backward(const sfgs_backward_args* a) {
   char* aptr = a->scratch_alloc(a->scratch_user, abytes);
   if (!aptr) return fail(SFGS_E_ALLOC, "backward: scratch allocator returned NULL");
   float* acc = (float*)sfgs_align_ptr(aptr);
+  PROF_BEGIN(ST_BWD_ZERO);
   CU(cudaMemsetAsync(acc, 0, (size_t)P * 16 * sizeof(float), st));
   if (a->ED > 0) CU(cudaMemsetAsync(a->dL_dextra, 0, (size_t)P * a->ED * sizeof(float), st));
+  PROF_END();
 
   if (a->R > 0) {
+    PROF_BEGIN(ST_RENDER_BWD);
     sfgs_launch_render_bwd(a, g, im, b, acc, st);
+    PROF_END();
     STAGE_CHECK("render_bwd");
   }
+  PROF_BEGIN(ST_GAUSS_BWD);
   sfgs_launch_gauss_bwd(a, g, focal_x, focal_y, acc, st);
+  PROF_END();
   STAGE_CHECK("gauss_bwd");
   return SFGS_OK;
+}
+
+size_t sfgs_sizeof(int which) {
+  switch (which) {
+    case 0: return sizeof(sfgs_forward_args);
+    case 1: return sizeof(sfgs_backward_args);
+    case 2: return sizeof(sfgs_geom_view);
+    case 3: return sizeof(sfgs_image_view);
+    case 4: return sizeof(sfgs_binning_view);
+    default: return 0;
+  }
+}
+
+int sfgs_profile_enable(int on) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  g_prof.collect();
+  g_prof.on = on != 0;
+  if (on) for (int i = 0; i < ST_COUNT; i++) { g_prof.ms[i] = 0; g_prof.n[i] = 0; }
+  return SFGS_OK;
+}
+
+int sfgs_profile_read(double* ms_total, long long* launches, int n) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  g_prof.collect();
+  for (int i = 0; i < n && i < ST_COUNT; i++) { if (ms_total) ms_total[i] = g_prof.ms[i]; if (launches) launches[i] = g_prof.n[i]; }
+  return ST_COUNT;
 }
 
 int sfgs_mark_visible(int P, const float* means3D, const float* viewmatrix, const float* projmatrix,

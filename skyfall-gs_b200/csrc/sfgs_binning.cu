@@ -63,6 +63,8 @@ tile_scan_kernel(int tiles, const uint32_t* __restrict__ tile_count, uint2* __re
     hdr[HDR_R] = R;
     hdr[HDR_OVERFLOW] = ((unsigned long long)R > capacity) ? 1u : 0u;
     hdr[HDR_MAXTILE] = maxlen_s;
+    hdr[HDR_CAP_LO] = (uint32_t)(capacity & 0xffffffffull);
+    hdr[HDR_CAP_HI] = (uint32_t)(capacity >> 32);
   }
 }
 
@@ -163,7 +165,8 @@ __device__ void radix_global(uint64_t* a, uint64_t* b, int n) {
 
 __global__ void __launch_bounds__(SORT_THREADS)
 tile_sort_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ hdr, uint64_t* __restrict__ keys,
-                 uint64_t* __restrict__ keys_tmp, uint32_t* __restrict__ point_list) {
+                 uint64_t* __restrict__ keys_tmp, uint32_t* __restrict__ point_list,
+                 const float* __restrict__ rec, int gx, unsigned char* __restrict__ inst_mask) {
   if (hdr[HDR_OVERFLOW]) return;
   __shared__ uint64_t s[SORT_SMEM_KEYS];
   const uint2 rg = ranges[blockIdx.x];
@@ -184,6 +187,14 @@ tile_sort_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
     radix_global(bucket, keys_tmp + rg.x, n);
     for (int i = threadIdx.x; i < n; i += SORT_THREADS) point_list[rg.x + i] = (uint32_t)bucket[i];
   }
+  // reach mask of every sorted instance (shared by the forward and backward blend kernels)
+  const int tile_px = (blockIdx.x % gx) * SFGS_TILE, tile_py = (blockIdx.x / gx) * SFGS_TILE;
+  for (int i = threadIdx.x; i < n; i += SORT_THREADS) {
+    const uint32_t id = (uint32_t)bucket[i];
+    const float4 r0 = *reinterpret_cast<const float4*>(rec + (size_t)id * REC_FLOATS);
+    const float2 r1 = *reinterpret_cast<const float2*>(rec + (size_t)id * REC_FLOATS + 4);
+    inst_mask[rg.x + i] = (unsigned char)reach_mask(r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, tile_px, tile_py);
+  }
 }
 
 }  // namespace
@@ -200,7 +211,8 @@ void sfgs_launch_emit(int P, const int* radii, const GeomLayout& g, const ImageL
                                                    im.tile_cursor, im.hdr, b.keys);
 }
 
-void sfgs_launch_tile_sort(const ImageLayout& im, const BinningLayout& b, cudaStream_t st) {
+void sfgs_launch_tile_sort(const GeomLayout& g, const ImageLayout& im, const BinningLayout& b, cudaStream_t st) {
   SFGS_COUNT_LAUNCH();
-  tile_sort_kernel<<<im.tiles, SORT_THREADS, 0, st>>>(im.ranges, im.hdr, b.keys, b.keys_tmp, b.point_list);
+  tile_sort_kernel<<<im.tiles, SORT_THREADS, 0, st>>>(im.ranges, im.hdr, b.keys, b.keys_tmp, b.point_list, g.rec,
+                                                      im.tiles_x, b.inst_mask);
 }

@@ -75,7 +75,8 @@ __device__ __forceinline__ float butterfly16(const float v[16], int lane) {
 
 template <bool HAS_EXTRA>
 __global__ void __launch_bounds__(BWD_THREADS)
-render_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W, int H, int ED,
+render_bwd_kernel(const uint2* __restrict__ ranges, const char* __restrict__ binning_base,
+                  const uint32_t* __restrict__ hdr, int W, int H, int ED,
                   const float* __restrict__ bg_color, const float* __restrict__ rec,
                   const float* __restrict__ extras, const float* __restrict__ accum_alphas,
                   const uint32_t* __restrict__ n_contrib, const float* __restrict__ dL_dpixels,
@@ -87,6 +88,13 @@ render_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
   __shared__ __align__(16) float s_part[BWD_WARPS][BWD_BATCH][16];        // 32 KB
   __shared__ unsigned long long s_mask[BWD_WARPS];
   __shared__ uint32_t s_maxc[BWD_WARPS];
+  __shared__ uint32_t s_bits[2][BWD_WARPS][BWD_BATCH / 32];
+
+  // the binning buffer layout depends on the capacity the forward used; it is recorded in the image header
+  const unsigned long long cap = ((unsigned long long)hdr[HDR_CAP_HI] << 32) | hdr[HDR_CAP_LO];
+  const BinningLayout bl(const_cast<char*>(binning_base), (size_t)cap);
+  const uint32_t* __restrict__ point_list = bl.point_list;
+  const unsigned char* __restrict__ inst_mask = bl.inst_mask;
 
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int tiles_x = (W + SFGS_TILE - 1) / SFGS_TILE;
@@ -142,17 +150,30 @@ render_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
   if (used == 0) return;
   const int nbatches = (used + BWD_BATCH - 1) / BWD_BATCH;
 
-  // batch b holds positions used-1-b*BATCH-e, e = 0..BATCH-1 (back to front)
+  // batch b holds positions used-1-b*BATCH-e, e = 0..BATCH-1 (back to front); thread e stages record e
   auto issue = [&](int batch, int stage) {
-    const int c = tid;                      // 64 records x 4 quarters = 256 copies
-    const int e = c >> 2, q = c & 3;
-    const int pos = used - 1 - batch * BWD_BATCH - e;
-    if (pos >= 0) {
-      const uint32_t id = point_list[range.x + pos];
-      cp_async16(&s_rec[stage][e][q], rec + (size_t)id * REC_FLOATS + q * 4);
-      if (q == 0) s_id[stage][e] = id;
+    unsigned m = 0;
+    if (tid < BWD_BATCH) {
+      const int pos = used - 1 - batch * BWD_BATCH - tid;
+      if (pos >= 0) {
+        m = inst_mask[range.x + pos];
+        if (m) {
+          const uint32_t id = point_list[range.x + pos];
+          const float* src = rec + (size_t)id * REC_FLOATS;
+#pragma unroll
+          for (int q = 0; q < 4; q++) cp_async16(&s_rec[stage][tid][q], src + q * 4);
+          s_id[stage][tid] = id;
+        }
+      }
     }
     cp_async_commit();
+    if (tid < BWD_BATCH) {
+#pragma unroll
+      for (int blk = 0; blk < BWD_WARPS; blk++) {
+        const unsigned word = __ballot_sync(0xffffffffu, (m >> blk) & 1u);
+        if (lane == 0) s_bits[stage][blk][wid] = word;
+      }
+    }
   };
 
   issue(0, 0);
@@ -165,10 +186,15 @@ render_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
     const int cnt = min(BWD_BATCH, first_pos + 1);
     unsigned long long mymask = 0ull;
 
-    // first entry this warp can use: pos < wmax  <=>  e > first_pos - wmax
+    // entries this warp can use: reach bit set and pos < wmax  <=>  e >= first_pos - wmax + 1
     int e0 = first_pos - (int)wmax + 1;
     if (e0 < 0) e0 = 0;
-    for (int e = e0; e < cnt; e++) {
+    for (int word = e0 >> 5; word < BWD_BATCH / 32; word++) {
+     unsigned bits = s_bits[stage][wid][word];
+     if (word == (e0 >> 5)) bits &= 0xffffffffu << (e0 & 31);
+     while (bits) {
+      const int e = word * 32 + __ffs(bits) - 1;
+      bits &= bits - 1;
       const int pos = first_pos - e;
       const float4 ra = s_rec[stage][e][0];   // mx, my, con.x, con.y
       const float4 rb = s_rec[stage][e][1];   // con.z, opac, depth
@@ -225,6 +251,7 @@ render_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
       const float z = butterfly16(v, lane);
       if ((lane & 1) == 0) s_part[wid][e][lane >> 1] = z;
       mymask |= (1ull << e);
+     }
     }
     if (lane == 0) s_mask[wid] = mymask;
     __syncthreads();
@@ -256,11 +283,13 @@ void sfgs_launch_render_bwd(const sfgs_backward_args* a, const GeomLayout& g, co
   SFGS_COUNT_LAUNCH();
   if (a->ED > 0)
     render_bwd_kernel<true><<<grid, BWD_THREADS, 0, st>>>(
-        im.ranges, b.point_list, a->width, a->height, a->ED, a->background, g.rec, a->extra_attrs, a->accum_alphas,
+        im.ranges, (const char*)b.point_list, im.hdr, a->width, a->height, a->ED, a->background, g.rec, a->extra_attrs,
+        a->accum_alphas,
         im.n_contrib, a->dL_dpix, a->dL_dpix_depth, a->dL_dpix_norm, a->dL_dpix_alpha, a->dL_dpix_extra, acc,
         a->dL_dextra);
   else
     render_bwd_kernel<false><<<grid, BWD_THREADS, 0, st>>>(
-        im.ranges, b.point_list, a->width, a->height, 0, a->background, g.rec, nullptr, a->accum_alphas,
+        im.ranges, (const char*)b.point_list, im.hdr, a->width, a->height, 0, a->background, g.rec, nullptr,
+        a->accum_alphas,
         im.n_contrib, a->dL_dpix, a->dL_dpix_depth, a->dL_dpix_norm, a->dL_dpix_alpha, nullptr, acc, nullptr);
 }

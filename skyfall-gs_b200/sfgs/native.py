@@ -81,8 +81,10 @@ EXPORTS = [
     "sfgs_geom_bytes", "sfgs_image_bytes", "sfgs_binning_bytes",
     "sfgs_geom_layout", "sfgs_image_layout", "sfgs_binning_layout", "sfgs_last_capacity",
     "sfgs_fusedssim_forward", "sfgs_fusedssim_backward", "sfgs_dist2_knn3",
-    "sfgs_last_error", "sfgs_version", "sfgs_launch_count",
+    "sfgs_last_error", "sfgs_version", "sfgs_launch_count", "sfgs_profile_enable", "sfgs_profile_read", "sfgs_sizeof",
 ]
+STAGE_NAMES = ["fwd_zero", "preprocess", "tile_scan", "emit_keys", "tile_sort", "render_fwd", "bwd_zero", "render_bwd",
+               "gauss_bwd"]
 
 _lib = None
 
@@ -121,8 +123,27 @@ def lib() -> C.CDLL:
     L.sfgs_last_error.argtypes = []; L.sfgs_last_error.restype = C.c_char_p
     L.sfgs_version.argtypes = []; L.sfgs_version.restype = C.c_int
     L.sfgs_launch_count.argtypes = []; L.sfgs_launch_count.restype = C.c_longlong
+    L.sfgs_sizeof.argtypes = [C.c_int]; L.sfgs_sizeof.restype = C.c_size_t
+    L.sfgs_profile_enable.argtypes = [C.c_int]; L.sfgs_profile_enable.restype = C.c_int
+    L.sfgs_profile_read.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_longlong), C.c_int]
+    L.sfgs_profile_read.restype = C.c_int
+    for which, st in enumerate((ForwardArgs, BackwardArgs, GeomView, ImageView, BinningView)):
+        if L.sfgs_sizeof(which) != C.sizeof(st):
+            raise ImportError(f"ABI mismatch: {st.__name__} is {C.sizeof(st)} bytes here, {L.sfgs_sizeof(which)} in {LIB_PATH}")
     _lib = L
     return L
+
+
+def profile_enable(on: bool) -> None:
+    lib().sfgs_profile_enable(1 if on else 0)
+
+
+def profile_read() -> dict:
+    """{stage: (total_ms, launches)} accumulated since profile_enable(True)."""
+    ms = (C.c_double * len(STAGE_NAMES))()
+    cnt = (C.c_longlong * len(STAGE_NAMES))()
+    lib().sfgs_profile_read(ms, cnt, len(STAGE_NAMES))
+    return {name: (ms[i], cnt[i]) for i, name in enumerate(STAGE_NAMES)}
 
 
 def last_error() -> str:
