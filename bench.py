@@ -65,40 +65,52 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    """SM clock / throttle reasons read through NVML while the GPU is under load.  Sampling happens in the
+    un-timed gap between two steps of the timed loop (the previous step's backward kernels are still
+    running then): polling from a second thread or process DURING a step stalls the driver and was
+    measured to inflate the median step from 2.1 ms to 4.4-4.7 ms, with 30-70 ms outliers."""
 
     def __init__(self, index: int):
-        self.index = index
-        self.rows = []
-        self.proc = None
-
-    def start(self):
-        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-             "clocks_event_reasons.sw_power_cap")
+        self.sm, self.reasons, self.max_mhz, self.nv = [], set(), None, None
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and all(v.strip().isdigit() for v in vis.split(",")) else index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.nv = pynvml
         except Exception:  # noqa: BLE001
-            self.proc = None
+            self.nv = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+    def sample(self):
+        nv = self.nv
+        if nv is None:
+            return
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+        try:
+            self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+            r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+            for k, bit in names.items():
+                if r & bit:
+                    self.reasons.add(k)
+        except Exception:  # noqa: BLE001
+            pass
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+        out = {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.max_mhz,
+               "reasons": sorted(self.reasons) if self.sm else ["not sampled"], "samples": len(self.sm),
+               "source": "NVML, sampled between steps of the timed loop while the previous step's kernels run"}
+        if self.nv is not None:
+            try:
+                self.nv.nvmlShutdown()
+            except Exception:  # noqa: BLE001
+                pass
+            self.nv = None
+        return out
 
 
 def camera_for_rank(rank: int, world: int) -> S.Camera:
@@ -170,12 +182,14 @@ def step_ref(d, cam):
     return f, g
 
 
-def timed_steps(step_fn, steps, warmup, flush, dev):
+def timed_steps(step_fn, steps, warmup, flush, dev, between=None):
     for _ in range(warmup):
         step_fn()
     torch.cuda.synchronize(dev)
     evs = []
-    for _ in range(steps):
+    for i in range(steps):
+        if between is not None and i % 4 == 2:
+            between()          # un-timed gap: the previous step's backward is still executing
         flush()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
@@ -183,7 +197,12 @@ def timed_steps(step_fn, steps, warmup, flush, dev):
         b.record()
         evs.append((a, b))
     torch.cuda.synchronize(dev)
-    return [a.elapsed_time(b) for a, b in evs]   # ms per step
+    ms = [a.elapsed_time(b) for a, b in evs]   # ms per step
+    if os.environ.get("SFGS_BENCH_VERBOSE"):
+        srt = sorted(ms)
+        print(f"[bench] steps={steps} min={srt[0]:.3f} med={srt[len(srt) // 2]:.3f} max={srt[-1]:.3f} ms; "
+              + " ".join(f"{m:.2f}" for m in ms), file=sys.stderr)
+    return ms
 
 
 # ----------------------------------------------------------------------------- public-API leg ("e2e")
@@ -293,6 +312,7 @@ def main():
     ap.add_argument("--shard", default="views", choices=["views", "tilerows"])
     ap.add_argument("--P", type=int, default=P_GAUSS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-clocks", action="store_true", help="do not poll nvidia-smi during the timed region")
     args = ap.parse_args()
     steps, warmup = max(1, args.steps), max(3, args.warmup)
 
@@ -333,8 +353,7 @@ def main():
         dist.barrier()
     torch.cuda.synchronize(dev)
     launches0 = native.lib().sfgs_launch_count() if args.impl == "ours" else 0
-    sampler.start()
-    ms = timed_steps(step, steps, warmup, flush, dev)
+    ms = timed_steps(step, steps, warmup, flush, dev, between=None if args.no_clocks else sampler.sample)
     clocks = sampler.stop()
     launches = (native.lib().sfgs_launch_count() - launches0) if args.impl == "ours" else None
     total_ms = torch.tensor([sum(ms)], dtype=torch.float64, device=dev)

@@ -63,6 +63,9 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if jobs:
         with ThreadPoolExecutor(max_workers=min(8, len(jobs))) as ex:
             list(ex.map(run, jobs))
+    for stale in os.listdir(OBJDIR):   # objects whose source was removed must not be linked
+        if stale.endswith(".o") and os.path.join(OBJDIR, stale) not in objs:
+            os.remove(os.path.join(OBJDIR, stale))
     if jobs or force or _newer(objs, LIB):
         run([nvcc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"])
     return LIB

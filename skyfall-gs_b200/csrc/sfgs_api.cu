@@ -18,13 +18,13 @@
 
 long long g_sfgs_launches = 0;
 
-void sfgs_launch_preprocess(const sfgs_forward_args* a, const GeomLayout& g, const ImageLayout& im, float focal_x,
-                            float focal_y, cudaStream_t st);
+void sfgs_launch_preprocess(const sfgs_forward_args* a, const GeomLayout& g, const ImageLayout& im,
+                            const BinningLayout& b, unsigned long long capacity, float focal_x, float focal_y,
+                            cudaStream_t st);
 void sfgs_launch_mark_visible(int P, const float* means3D, const float* viewmatrix, unsigned char* present,
                               cudaStream_t st);
 void sfgs_launch_tile_scan(const ImageLayout& im, unsigned long long capacity, cudaStream_t st);
-void sfgs_launch_emit(int P, const int* radii, const GeomLayout& g, const ImageLayout& im, const BinningLayout& b,
-                      cudaStream_t st);
+void sfgs_launch_scatter(const ImageLayout& im, const BinningLayout& b, unsigned long long capacity, cudaStream_t st);
 void sfgs_launch_tile_sort(const GeomLayout& g, const ImageLayout& im, const BinningLayout& b, cudaStream_t st);
 void sfgs_launch_render_fwd(const sfgs_forward_args* a, const GeomLayout& g, const ImageLayout& im,
                             const BinningLayout& b, cudaStream_t st);
@@ -174,19 +174,6 @@ int sfgs_rasterize_forward(const sfgs_forward_args* a) {
   if (!iptr) return fail(SFGS_E_ALLOC, "forward: image allocator returned NULL");
   ImageLayout im(sfgs_align_ptr(iptr), a->width, a->height);
 
-  // tile histogram + header start at zero
-  PROF_BEGIN(ST_FWD_ZERO);
-  CU(cudaMemsetAsync(im.hdr, 0, IMG_HDR_WORDS * sizeof(uint32_t), st));
-  CU(cudaMemsetAsync(im.tile_count, 0, (size_t)im.tiles * sizeof(uint32_t), st));
-  PROF_END();
-
-  if (P > 0) {
-    PROF_BEGIN(ST_PREPROCESS);
-    sfgs_launch_preprocess(a, g, im, focal_x, focal_y, st);
-    PROF_END();
-    STAGE_CHECK("preprocess");
-  }
-
   long long capacity = a->capacity_hint;
   if (capacity <= 0) {
     const long long last = g_last_R.load();
@@ -202,15 +189,27 @@ int sfgs_rasterize_forward(const sfgs_forward_args* a) {
     if (!bptr) return fail(SFGS_E_ALLOC, "forward: binning allocator returned NULL");
     BinningLayout b(sfgs_align_ptr(bptr), (size_t)capacity);
 
+    // tile histogram + header start at zero
+    PROF_BEGIN(ST_FWD_ZERO);
+    CU(cudaMemsetAsync(im.hdr, 0, IMG_HDR_WORDS * sizeof(uint32_t), st));
+    CU(cudaMemsetAsync(im.tile_count, 0, (size_t)im.tiles * sizeof(uint32_t), st));
+    PROF_END();
+
+    if (P > 0) {
+      PROF_BEGIN(ST_PREPROCESS);
+      sfgs_launch_preprocess(a, g, im, b, (unsigned long long)capacity, focal_x, focal_y, st);
+      PROF_END();
+      STAGE_CHECK("preprocess");
+    }
     PROF_BEGIN(ST_SCAN);
     sfgs_launch_tile_scan(im, (unsigned long long)capacity, st);
     PROF_END();
     STAGE_CHECK("tile_scan");
     if (P > 0) {
       PROF_BEGIN(ST_EMIT);
-      sfgs_launch_emit(P, a->radii, g, im, b, st);
+      sfgs_launch_scatter(im, b, (unsigned long long)capacity, st);
       PROF_END();
-      STAGE_CHECK("emit_keys");
+      STAGE_CHECK("scatter_keys");
       PROF_BEGIN(ST_SORT);
       sfgs_launch_tile_sort(g, im, b, st);
       PROF_END();
@@ -226,7 +225,7 @@ int sfgs_rasterize_forward(const sfgs_forward_args* a) {
     R = (long long)hhdr[HDR_R];
     if (!hhdr[HDR_OVERFLOW]) break;
     if (attempt == 2) return fail(SFGS_E_CUDA, "forward: binning capacity overflow persisted");
-    capacity = R + R / 16 + 4096;   // exact count is now known; re-run the tail of the pipeline
+    capacity = R + R / 16 + 4096;   // the exact count is now known; run the pipeline again with room for it
   }
   g_last_R.store(R);
   g_last_capacity.store(capacity);

@@ -68,128 +68,114 @@ tile_scan_kernel(int tiles, const uint32_t* __restrict__ tile_count, uint2* __re
   }
 }
 
-// ---- key emission ------------------------------------------------------------
+// ---- key scatter ---------------------------------------------------------------
+// One thread per unsorted instance {gaussian, depth bits, tile, slot-in-tile}: no atomics, perfectly balanced.
 __global__ void __launch_bounds__(256)
-emit_keys_kernel(int P, const int* __restrict__ radii, const float* __restrict__ rec, int gx, int gy,
-                 const uint2* __restrict__ ranges, uint32_t* __restrict__ tile_cursor,
-                 const uint32_t* __restrict__ hdr, uint64_t* __restrict__ keys) {
+scatter_keys_kernel(const uint4* __restrict__ tmp, const uint2* __restrict__ ranges, const uint32_t* __restrict__ hdr,
+                    uint64_t* __restrict__ keys) {
   if (hdr[HDR_OVERFLOW]) return;
-  const int idx = blockIdx.x * 256 + threadIdx.x;
-  if (idx >= P) return;
-  const int radius = radii[idx];
-  if (radius <= 0) return;
-  const float4 r0 = *reinterpret_cast<const float4*>(rec + (size_t)idx * REC_FLOATS);
-  const float depth = rec[(size_t)idx * REC_FLOATS + REC_DEPTH];
-  const TileRect r = tile_rect(r0.x, r0.y, radius, gx, gy);
-  const uint64_t key = ((uint64_t)__float_as_uint(depth) << 32) | (uint32_t)idx;
-  for (int y = r.y0; y < r.y1; y++)
-    for (int x = r.x0; x < r.x1; x++) {
-      const int t = y * gx + x;
-      const uint32_t pos = atomicAdd(&tile_cursor[t], 1u);
-      keys[ranges[t].x + pos] = key;
-    }
+  const uint32_t i = blockIdx.x * 256u + threadIdx.x;
+  if (i >= hdr[HDR_R]) return;
+  const uint4 t = tmp[i];
+  keys[ranges[t.z].x + t.w] = ((uint64_t)t.y << 32) | t.x;
 }
 
 // ---- per-tile sort -------------------------------------------------------------
-// One CTA per tile. Lists that fit the shared-memory window are sorted with a
-// bitonic network on 64-bit keys (padded with ~0); longer lists fall back to an
-// in-CTA LSD radix sort that ping-pongs through global memory.
-constexpr int SORT_THREADS = 256;
-constexpr int SORT_SMEM_KEYS = 4096;   // 32 KB window
-
+// One CTA per tile, two launches over the same grid: a light variant (128 threads, 1024-key window) for
+// the common short lists and a heavy one (256 threads, 4096-key window, global radix fallback beyond that);
+// a CTA whose tile belongs to the other class exits at once.  Lists inside the window are sorted with a
+// bitonic network on 64-bit (depth_bits << 32 | id) keys padded with ~0.
+template <int THREADS>
 __device__ __forceinline__ void bitonic_smem(uint64_t* s, int n2) {
   for (int k = 2; k <= n2; k <<= 1) {
     for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int i = threadIdx.x; i < n2; i += SORT_THREADS) {
-        const int l = i ^ j;
-        if (l > i) {
-          const uint64_t a = s[i], b = s[l];
-          const bool up = ((i & k) == 0);
-          if ((a > b) == up) { s[i] = b; s[l] = a; }
-        }
+      for (int i = threadIdx.x; i < (n2 >> 1); i += THREADS) {
+        // i-th compare-exchange of this stage: lower index has bit j clear
+        const int lo = ((i & ~(j - 1)) << 1) | (i & (j - 1));
+        const int hi = lo | j;
+        const uint64_t a = s[lo], b = s[hi];
+        const bool up = ((lo & k) == 0);
+        if ((a > b) == up) { s[lo] = b; s[hi] = a; }
       }
       __syncthreads();
     }
   }
 }
 
-// stable LSD radix sort of n 64-bit keys, 8 bits per pass, one CTA, global ping-pong
-__device__ void radix_global(uint64_t* a, uint64_t* b, int n) {
-  __shared__ uint32_t hist[256];
-  __shared__ uint32_t digit_base[256];
-  __shared__ uint32_t warp_digit_cnt[SORT_THREADS / 32][256];  // 8 KB
+// stable LSD radix sort of n 64-bit keys, 8 bits per pass, one CTA of 256 threads, global ping-pong
+__device__ void radix_global(uint64_t* a, uint64_t* b, int n, uint32_t* scratch /* >= 2560 words of shared memory */) {
+  constexpr int T = 256;
+  uint32_t* hist = scratch;                       // [256]
+  uint32_t* digit_base = scratch + 256;           // [256]
+  uint32_t (*warp_digit_cnt)[256] = reinterpret_cast<uint32_t (*)[256]>(scratch + 512);   // [8][256]
+  __shared__ int skip;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   uint64_t* src = a; uint64_t* dst = b;
   for (int pass = 0; pass < 8; pass++) {
     const int shift = pass * 8;
-    hist[tid] = 0;   // SORT_THREADS == 256
-    __syncthreads();
-    for (int i = tid; i < n; i += SORT_THREADS) atomicAdd(&hist[(src[i] >> shift) & 255u], 1u);
-    __syncthreads();
-    // skip passes whose digit is constant over the bucket
-    __shared__ int skip;
+    hist[tid] = 0;
     if (tid == 0) skip = 0;
     __syncthreads();
-    if (hist[tid] == (uint32_t)n) skip = 1;
+    for (int i = tid; i < n; i += T) atomicAdd(&hist[(src[i] >> shift) & 255u], 1u);
+    __syncthreads();
+    if (hist[tid] == (uint32_t)n) skip = 1;   // digit constant over the bucket: nothing to do
     __syncthreads();
     if (skip) { __syncthreads(); continue; }
     if (tid == 0) { uint32_t s = 0; for (int d = 0; d < 256; d++) { digit_base[d] = s; s += hist[d]; } }
     __syncthreads();
-    for (int base = 0; base < n; base += SORT_THREADS) {
+    for (int base = 0; base < n; base += T) {
       for (int d = lane; d < 256; d += 32) warp_digit_cnt[wid][d] = 0;
       __syncwarp();
       const int i = base + tid;
       const bool valid = i < n;
-      uint64_t key = valid ? src[i] : 0;
+      const uint64_t key = valid ? src[i] : 0;
       const uint32_t d = (uint32_t)(key >> shift) & 255u;
-      // rank among earlier lanes of this warp with the same digit
       const unsigned peers = __match_any_sync(0xffffffffu, valid ? d : 0xffffffffu);
       const uint32_t rank_in_warp = __popc(peers & ((1u << lane) - 1u));
       if (valid && rank_in_warp == 0) warp_digit_cnt[wid][d] = __popc(peers);
       __syncthreads();
-      // exclusive prefix over warps for my digit
       uint32_t before = 0;
       if (valid) for (int w = 0; w < wid; w++) before += warp_digit_cnt[w][d];
       if (valid) dst[digit_base[d] + before + rank_in_warp] = key;
       __syncthreads();
-      // advance digit bases by this chunk's totals
-      { uint32_t tot = 0; for (int w = 0; w < SORT_THREADS / 32; w++) tot += warp_digit_cnt[w][tid]; digit_base[tid] += tot; }
+      { uint32_t tot = 0; for (int w = 0; w < T / 32; w++) tot += warp_digit_cnt[w][tid]; digit_base[tid] += tot; }
       __syncthreads();
     }
     uint64_t* t = src; src = dst; dst = t;
     __syncthreads();
   }
-  if (src != a) { for (int i = tid; i < n; i += SORT_THREADS) a[i] = src[i]; }
+  if (src != a) { for (int i = tid; i < n; i += T) a[i] = src[i]; }
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(SORT_THREADS)
+template <int THREADS, int WINDOW, int MIN_N>
+__global__ void __launch_bounds__(THREADS)
 tile_sort_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ hdr, uint64_t* __restrict__ keys,
                  uint64_t* __restrict__ keys_tmp, uint32_t* __restrict__ point_list,
                  const float* __restrict__ rec, int gx, unsigned char* __restrict__ inst_mask) {
   if (hdr[HDR_OVERFLOW]) return;
-  __shared__ uint64_t s[SORT_SMEM_KEYS];
   const uint2 rg = ranges[blockIdx.x];
   const int n = (int)(rg.y - rg.x);
-  if (n == 0) return;
+  if (n <= MIN_N || (MIN_N == 0 && n > WINDOW)) return;   // other variant's tile (or empty)
+  __shared__ uint64_t s[WINDOW];
   uint64_t* bucket = keys + rg.x;
-  if (n <= SORT_SMEM_KEYS) {
-    int n2 = 1; while (n2 < n) n2 <<= 1;
-    for (int i = threadIdx.x; i < n2; i += SORT_THREADS) s[i] = (i < n) ? bucket[i] : ~0ull;
+  if (n <= WINDOW) {
+    int n2 = 2; while (n2 < n) n2 <<= 1;
+    for (int i = threadIdx.x; i < n2; i += THREADS) s[i] = (i < n) ? bucket[i] : ~0ull;
     __syncthreads();
-    bitonic_smem(s, n2);
-    for (int i = threadIdx.x; i < n; i += SORT_THREADS) {
+    bitonic_smem<THREADS>(s, n2);
+    for (int i = threadIdx.x; i < n; i += THREADS) {
       const uint64_t k = s[i];
       bucket[i] = k;
       point_list[rg.x + i] = (uint32_t)k;
     }
-  } else {
-    radix_global(bucket, keys_tmp + rg.x, n);
-    for (int i = threadIdx.x; i < n; i += SORT_THREADS) point_list[rg.x + i] = (uint32_t)bucket[i];
+  } else if (THREADS == 256) {
+    radix_global(bucket, keys_tmp + rg.x, n, reinterpret_cast<uint32_t*>(s));
+    for (int i = threadIdx.x; i < n; i += THREADS) point_list[rg.x + i] = (uint32_t)bucket[i];
   }
   // reach mask of every sorted instance (shared by the forward and backward blend kernels)
   const int tile_px = (blockIdx.x % gx) * SFGS_TILE, tile_py = (blockIdx.x / gx) * SFGS_TILE;
-  for (int i = threadIdx.x; i < n; i += SORT_THREADS) {
+  for (int i = threadIdx.x; i < n; i += THREADS) {
     const uint32_t id = (uint32_t)bucket[i];
     const float4 r0 = *reinterpret_cast<const float4*>(rec + (size_t)id * REC_FLOATS);
     const float2 r1 = *reinterpret_cast<const float2*>(rec + (size_t)id * REC_FLOATS + 4);
@@ -204,15 +190,18 @@ void sfgs_launch_tile_scan(const ImageLayout& im, unsigned long long capacity, c
   tile_scan_kernel<<<1, SCAN_THREADS, 0, st>>>(im.tiles, im.tile_count, im.ranges, im.tile_cursor, im.hdr, capacity);
 }
 
-void sfgs_launch_emit(int P, const int* radii, const GeomLayout& g, const ImageLayout& im, const BinningLayout& b,
-                      cudaStream_t st) {
+void sfgs_launch_scatter(const ImageLayout& im, const BinningLayout& b, unsigned long long capacity, cudaStream_t st) {
   SFGS_COUNT_LAUNCH();
-  emit_keys_kernel<<<(P + 255) / 256, 256, 0, st>>>(P, radii, g.rec, im.tiles_x, im.tiles_y, im.ranges,
-                                                   im.tile_cursor, im.hdr, b.keys);
+  const unsigned blocks = (unsigned)((capacity + 255) / 256);
+  if (blocks == 0) return;
+  scatter_keys_kernel<<<blocks, 256, 0, st>>>(b.tmp, im.ranges, im.hdr, b.keys);
 }
 
 void sfgs_launch_tile_sort(const GeomLayout& g, const ImageLayout& im, const BinningLayout& b, cudaStream_t st) {
   SFGS_COUNT_LAUNCH();
-  tile_sort_kernel<<<im.tiles, SORT_THREADS, 0, st>>>(im.ranges, im.hdr, b.keys, b.keys_tmp, b.point_list, g.rec,
-                                                      im.tiles_x, b.inst_mask);
+  tile_sort_kernel<128, 1024, 0><<<im.tiles, 128, 0, st>>>(im.ranges, im.hdr, b.keys, b.keys_tmp, b.point_list, g.rec,
+                                                           im.tiles_x, b.inst_mask);
+  SFGS_COUNT_LAUNCH();
+  tile_sort_kernel<256, 4096, 1024><<<im.tiles, 256, 0, st>>>(im.ranges, im.hdr, b.keys, b.keys_tmp, b.point_list,
+                                                              g.rec, im.tiles_x, b.inst_mask);
 }

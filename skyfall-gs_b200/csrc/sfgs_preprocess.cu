@@ -183,9 +183,13 @@ preprocess_kernel(int P, int D, int M,
                   float focal_x, float focal_y, float kernel_size, int gx, int gy,
                   int* __restrict__ radii, float* __restrict__ rec, float* __restrict__ cov3D_out,
                   unsigned char* __restrict__ clamped, uint32_t* __restrict__ tiles_touched,
-                  uint32_t* __restrict__ tile_count) {
-  const int idx = blockIdx.x * PRE_THREADS + threadIdx.x;
-  if (idx >= P) return;
+                  uint32_t* __restrict__ tile_count, uint32_t* __restrict__ hdr, uint4* __restrict__ tmp,
+                  unsigned long long capacity) {
+  const int idx_raw = blockIdx.x * PRE_THREADS + threadIdx.x;
+  const bool in_range = idx_raw < P;
+  const int idx = in_range ? idx_raw : P - 1;   // out-of-range lanes shadow the last Gaussian and write nothing
+  TileRect vis_rect = {0, 0, 0, 0};
+  float vis_depth = 0.f;
 
   const float px = means3D[3 * idx], py = means3D[3 * idx + 1], pz = means3D[3 * idx + 2];
   const float* vm = viewmatrix;
@@ -195,7 +199,7 @@ preprocess_kernel(int P, int D, int M,
   uint32_t out_tiles = 0;
 
   const float view_z = vm[2] * px + vm[6] * py + vm[10] * pz + vm[14];
-  if (view_z > 0.2f) {
+  if (in_range && view_z > 0.2f) {
     const float hx = pm[0] * px + pm[4] * py + pm[8] * pz + pm[12];
     const float hy = pm[1] * px + pm[5] * py + pm[9] * pz + pm[13];
     const float hw = pm[3] * px + pm[7] * py + pm[11] * pz + pm[15];
@@ -239,7 +243,22 @@ preprocess_kernel(int P, int D, int M,
         float rgb[3];
         unsigned cmask = 0;
         if (colors_precomp == nullptr) {
-          sh_to_rgb(D, shs + (size_t)idx * M * 3, px, py, pz, cam_pos[0], cam_pos[1], cam_pos[2], rgb, cmask);
+          const float* shp = shs + (size_t)idx * M * 3;
+          if (M == 16) {
+            // 192 contiguous, 16-byte aligned bytes per Gaussian: twelve 128-bit loads instead of 48 scalar ones
+            float shl[48];
+            const float4* s4 = reinterpret_cast<const float4*>(shp);
+            const int nq = D == 0 ? 1 : (D == 1 ? 3 : (D == 2 ? 7 : 12));   // float4s covering (D+1)^2 coefficients
+#pragma unroll
+            for (int k = 0; k < 12; k++) {
+              float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (k < nq) v = __ldg(s4 + k);
+              shl[4 * k] = v.x; shl[4 * k + 1] = v.y; shl[4 * k + 2] = v.z; shl[4 * k + 3] = v.w;
+            }
+            sh_to_rgb(D, shl, px, py, pz, cam_pos[0], cam_pos[1], cam_pos[2], rgb, cmask);
+          } else {
+            sh_to_rgb(D, shp, px, py, pz, cam_pos[0], cam_pos[1], cam_pos[2], rgb, cmask);
+          }
         } else {
           rgb[0] = colors_precomp[3 * idx]; rgb[1] = colors_precomp[3 * idx + 1]; rgb[2] = colors_precomp[3 * idx + 2];
         }
@@ -252,14 +271,53 @@ preprocess_kernel(int P, int D, int M,
         o[3] = make_float4(n[1], n[2], 0.f, 0.f);
         out_radius = iradius;
         out_tiles = ntiles;
-        // per-tile instance histogram (replaces the per-Gaussian prefix sum of the reference)
-        for (int y = r.y0; y < r.y1; y++)
-          for (int x = r.x0; x < r.x1; x++) atomicAdd(&tile_count[y * gx + x], 1u);
+        vis_rect = r;
+        vis_depth = view_z;
       }
     }
   }
-  radii[idx] = out_radius;
-  tiles_touched[idx] = out_tiles;
+  if (!in_range) out_tiles = 0;
+  if (in_range) {
+    radii[idx] = out_radius;
+    tiles_touched[idx] = out_tiles;
+  }
+  // ---- append this warp's tile instances to the unsorted list -----------------------------------
+  // One warp-aggregated atomic reserves the slots.  The warp's instances are then dealt out to the
+  // lanes round-robin (instance j -> owner found by a binary search over the inclusive prefix kept in
+  // shared memory), so a large splat no longer serialises its lane and 32 independent histogram
+  // atomics are in flight per step.  The histogram atomic (it replaces the per-Gaussian prefix sum of
+  // the reference) hands back the instance's slot inside its tile bucket: the later scatter needs none.
+  __shared__ uint32_t s_incl[PRE_THREADS];
+  __shared__ int4 s_rect[PRE_THREADS];      // x0, y0, width, depth bits
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned wbase = threadIdx.x & ~31u;
+  uint32_t incl = out_tiles;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= (unsigned)o) incl += y; }
+  const uint32_t warp_total = __shfl_sync(0xffffffffu, incl, 31);
+  if (warp_total == 0) return;
+  uint32_t warp_base = 0;
+  if (lane == 31) warp_base = atomicAdd(&hdr[HDR_TMP_COUNT], warp_total);
+  warp_base = __shfl_sync(0xffffffffu, warp_base, 31);
+  s_incl[threadIdx.x] = incl;
+  s_rect[threadIdx.x] = make_int4(vis_rect.x0, vis_rect.y0, vis_rect.x1 - vis_rect.x0, (int)__float_as_uint(vis_depth));
+  __syncwarp();
+  for (uint32_t j = lane; j < warp_total; j += 32) {
+    // owner = first lane whose inclusive prefix exceeds j
+    int lo = 0;
+#pragma unroll
+    for (int step = 16; step > 0; step >>= 1)
+      if (s_incl[wbase + lo + step - 1] <= j) lo += step;
+    const uint32_t excl = lo > 0 ? s_incl[wbase + lo - 1] : 0u;
+    const int4 rc = s_rect[wbase + lo];
+    const uint32_t k = j - excl;                       // k-th tile of the owner's rectangle, row-major
+    const uint32_t ty = k / (uint32_t)rc.z, tx = k - ty * (uint32_t)rc.z;
+    const uint32_t t = (uint32_t)(rc.y + (int)ty) * (uint32_t)gx + (uint32_t)(rc.x + (int)tx);
+    const uint32_t pos = atomicAdd(&tile_count[t], 1u);
+    const unsigned long long slot = (unsigned long long)warp_base + j;
+    const uint32_t gid = (uint32_t)(blockIdx.x * PRE_THREADS) + wbase + (uint32_t)lo;
+    if (slot < capacity) tmp[slot] = make_uint4(gid, (uint32_t)rc.w, t, pos);
+  }
 }
 
 __global__ void mark_visible_kernel(int P, const float* __restrict__ means3D,
@@ -274,14 +332,15 @@ __global__ void mark_visible_kernel(int P, const float* __restrict__ means3D,
 }  // namespace
 
 void sfgs_launch_preprocess(const sfgs_forward_args* a, const GeomLayout& g, const ImageLayout& im,
-                            float focal_x, float focal_y, cudaStream_t st) {
+                            const BinningLayout& b, unsigned long long capacity, float focal_x, float focal_y,
+                            cudaStream_t st) {
   const int blocks = (a->P + PRE_THREADS - 1) / PRE_THREADS;
   SFGS_COUNT_LAUNCH();
   preprocess_kernel<<<blocks, PRE_THREADS, 0, st>>>(
       a->P, a->D, a->M, a->means3D, a->scales, a->scale_modifier, a->rotations, a->opacities, a->shs,
       a->cov3D_precomp, a->norm3D_precomp, a->colors_precomp, a->viewmatrix, a->projmatrix, a->cam_pos,
       a->width, a->height, a->tan_fovx, a->tan_fovy, focal_x, focal_y, a->kernel_size, im.tiles_x, im.tiles_y,
-      a->radii, g.rec, g.cov3D, g.clamped, g.tiles_touched, im.tile_count);
+      a->radii, g.rec, g.cov3D, g.clamped, g.tiles_touched, im.tile_count, im.hdr, b.tmp, capacity);
 }
 
 void sfgs_launch_mark_visible(int P, const float* means3D, const float* viewmatrix, unsigned char* present,

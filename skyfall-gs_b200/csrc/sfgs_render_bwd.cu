@@ -211,7 +211,8 @@ render_bwd_kernel(const uint2* __restrict__ ranges, const char* __restrict__ bin
       if (active) {
         const float4 rc = s_rec[stage][e][2];   // r, g, b, nx
         const float4 rd = s_rec[stage][e][3];   // ny, nz
-        T = T / (1.f - alpha);
+        const float inv_1ma = __frcp_rn(1.f - alpha);   // shared by the T recovery and the background term
+        T = T * inv_1ma;
         const float weight = alpha * T;
         float g = rc.x * dLc0;
         g += rc.y * dLc1; g += rc.z * dLc2; g += rb.z * dLd;
@@ -231,7 +232,7 @@ render_bwd_kernel(const uint2* __restrict__ ranges, const char* __restrict__ bin
         }
         dL_dalpha *= T;
         last_alpha = alpha;
-        dL_dalpha += (-T_final / (1.f - alpha)) * bg_dot;
+        dL_dalpha += (-T_final * inv_1ma) * bg_dot;
 
         const float dL_dG = rb.y * dL_dalpha;
         const float gdx = G * dx, gdy = G * dy;

