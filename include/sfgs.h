@@ -96,6 +96,10 @@ typedef struct sfgs_forward_args {
   void* stream;       /* cudaStream_t */
   /* optional hint: expected number of tile instances (0 = let the library guess) */
   long long capacity_hint;
+  /* optional screen-space shard (multi-GPU tile-row sharding): only tile rows
+   * [tile_row_begin, tile_row_end) of the full tile grid are binned and blended, and only their pixels are
+   * written.  radii still report visibility in the FULL image.  0,0 = the whole image. */
+  int tile_row_begin, tile_row_end;
 } sfgs_forward_args;
 
 /* Returns num_rendered (>= 0) or a negative SFGS_E_* code. */
@@ -147,6 +151,8 @@ typedef struct sfgs_backward_args {
   sfgs_alloc_fn scratch_alloc; void* scratch_user;
   int debug;
   void* stream;
+  /* the same band the forward used (0,0 = whole image); gradients are then partial sums over the band */
+  int tile_row_begin, tile_row_end;
 } sfgs_backward_args;
 
 int sfgs_rasterize_backward(const sfgs_backward_args* a);

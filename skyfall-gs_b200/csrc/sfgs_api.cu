@@ -2,10 +2,13 @@
 //
 // Forward  = zero tile histogram -> preprocess -> tile scan -> key emission ->
 //            per-tile sort -> blend, all queued on the caller's stream with no
-//            host round trip in between; the only synchronisation is the read
-//            of num_rendered at the very end (the reference blocks on a
-//            cudaMemcpy in the middle of its forward, rasterizer_impl.cu:286-287,
-//            because it must size the binning buffer before it can continue).
+//            host round trip in between.  num_rendered is final after the tile
+//            scan; its 32-byte copy is queued there and the host waits on that
+//            event only, AFTER every kernel of the forward has been queued, so it
+//            returns while sort + blend are still running and the caller can queue
+//            the backward without a bubble (the reference blocks on a cudaMemcpy in
+//            the middle of its forward, rasterizer_impl.cu:286-287, because it must
+//            size the binning buffer before it can launch anything else).
 //            The binning buffer is sized from a running estimate instead and the
 //            tail of the pipeline is re-run in the rare case it was too small.
 // Backward = zero accumulators -> tile blend adjoint -> per-Gaussian adjoint.
@@ -100,10 +103,14 @@ std::mutex g_prof_mu;
 
 struct PinnedHdr {
   uint32_t* p = nullptr;
+  cudaEvent_t ev = nullptr;
   ~PinnedHdr() { /* leaked on purpose: the CUDA context may already be gone at exit */ }
   uint32_t* get() {
-    if (!p) { if (cudaHostAlloc((void**)&p, IMG_HDR_WORDS * sizeof(uint32_t), cudaHostAllocDefault) != cudaSuccess) p = nullptr; }
-    return p;
+    if (!p) {
+      if (cudaHostAlloc((void**)&p, IMG_HDR_WORDS * sizeof(uint32_t), cudaHostAllocDefault) != cudaSuccess) p = nullptr;
+      if (p && cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) { ev = nullptr; }
+    }
+    return (p && ev) ? p : nullptr;
   }
 };
 thread_local PinnedHdr t_hdr;
@@ -144,6 +151,7 @@ int sfgs_rasterize_forward(const sfgs_forward_args* a) {
   if (!a) return fail(SFGS_E_BADARG, "forward: null args");
   if (a->P < 0 || a->width <= 0 || a->height <= 0) return fail(SFGS_E_BADARG, "forward: bad sizes");
   if (a->ED < 0 || a->ED > SFGS_MAX_EXTRA) return fail(SFGS_E_BADARG, "forward: ED out of range");
+  if (a->tile_row_begin < 0 || a->tile_row_end < a->tile_row_begin) return fail(SFGS_E_BADARG, "forward: bad tile-row band");
   if (!a->out_color || !a->out_depth || !a->out_norm || !a->out_alpha || (a->P > 0 && !a->radii))
     return fail(SFGS_E_BADARG, "forward: null output");
   if (!a->geom_alloc || !a->binning_alloc || !a->image_alloc) return fail(SFGS_E_BADARG, "forward: null allocator");
@@ -205,6 +213,10 @@ int sfgs_rasterize_forward(const sfgs_forward_args* a) {
     sfgs_launch_tile_scan(im, (unsigned long long)capacity, st);
     PROF_END();
     STAGE_CHECK("tile_scan");
+    // num_rendered and the overflow flag are final after the scan: start their copy now and let the host wait
+    // on this event only, so it returns (and the caller can queue the backward) while sort + blend still run
+    CU(cudaMemcpyAsync(hhdr, im.hdr, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CU(cudaEventRecord(t_hdr.ev, st));
     if (P > 0) {
       PROF_BEGIN(ST_EMIT);
       sfgs_launch_scatter(im, b, (unsigned long long)capacity, st);
@@ -220,8 +232,8 @@ int sfgs_rasterize_forward(const sfgs_forward_args* a) {
     PROF_END();
     STAGE_CHECK("render_fwd");
 
-    CU(cudaMemcpyAsync(hhdr, im.hdr, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
+    CU(cudaEventSynchronize(t_hdr.ev));
+    if (debug) CU(cudaStreamSynchronize(st));
     R = (long long)hhdr[HDR_R];
     if (!hhdr[HDR_OVERFLOW]) break;
     if (attempt == 2) return fail(SFGS_E_CUDA, "forward: binning capacity overflow persisted");

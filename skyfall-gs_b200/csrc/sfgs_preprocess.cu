@@ -180,7 +180,7 @@ preprocess_kernel(int P, int D, int M,
                   const float* __restrict__ norm3D_precomp, const float* __restrict__ colors_precomp,
                   const float* __restrict__ viewmatrix, const float* __restrict__ projmatrix,
                   const float* __restrict__ cam_pos, int W, int H, float tan_fovx, float tan_fovy,
-                  float focal_x, float focal_y, float kernel_size, int gx, int gy,
+                  float focal_x, float focal_y, float kernel_size, int gx, int gy, int band0, int band1,
                   int* __restrict__ radii, float* __restrict__ rec, float* __restrict__ cov3D_out,
                   unsigned char* __restrict__ clamped, uint32_t* __restrict__ tiles_touched,
                   uint32_t* __restrict__ tile_count, uint32_t* __restrict__ hdr, uint4* __restrict__ tmp,
@@ -230,8 +230,12 @@ preprocess_kernel(int P, int D, int M,
       const float pix_x = ndc_to_pix(proj_x, W), pix_y = ndc_to_pix(proj_y, H);
       const int iradius = my_radius;
       const TileRect r = tile_rect(pix_x, pix_y, iradius, gx, gy);
-      const uint32_t ntiles = (uint32_t)((r.x1 - r.x0) * (r.y1 - r.y0));
-      if (ntiles != 0) {
+      const uint32_t ntiles_full = (uint32_t)((r.x1 - r.x0) * (r.y1 - r.y0));
+      // screen-space shard: this rank only bins the tile rows [band0, band1)
+      TileRect rb = r;
+      rb.y0 = max(r.y0, band0); rb.y1 = min(r.y1, band1);
+      const uint32_t ntiles = rb.y1 > rb.y0 ? (uint32_t)((rb.x1 - rb.x0) * (rb.y1 - rb.y0)) : 0u;
+      if (ntiles_full != 0) {
         float n[3];
         if (norm3D_precomp != nullptr) {
           n[0] = norm3D_precomp[3 * idx]; n[1] = norm3D_precomp[3 * idx + 1]; n[2] = norm3D_precomp[3 * idx + 2];
@@ -271,7 +275,7 @@ preprocess_kernel(int P, int D, int M,
         o[3] = make_float4(n[1], n[2], 0.f, 0.f);
         out_radius = iradius;
         out_tiles = ntiles;
-        vis_rect = r;
+        vis_rect = rb;
         vis_depth = view_z;
       }
     }
@@ -340,6 +344,8 @@ void sfgs_launch_preprocess(const sfgs_forward_args* a, const GeomLayout& g, con
       a->P, a->D, a->M, a->means3D, a->scales, a->scale_modifier, a->rotations, a->opacities, a->shs,
       a->cov3D_precomp, a->norm3D_precomp, a->colors_precomp, a->viewmatrix, a->projmatrix, a->cam_pos,
       a->width, a->height, a->tan_fovx, a->tan_fovy, focal_x, focal_y, a->kernel_size, im.tiles_x, im.tiles_y,
+      a->tile_row_end > a->tile_row_begin ? a->tile_row_begin : 0,
+      a->tile_row_end > a->tile_row_begin ? a->tile_row_end : im.tiles_y,
       a->radii, g.rec, g.cov3D, g.clamped, g.tiles_touched, im.tile_count, im.hdr, b.tmp, capacity);
 }
 

@@ -76,7 +76,7 @@ __device__ __forceinline__ float butterfly16(const float v[16], int lane) {
 template <bool HAS_EXTRA>
 __global__ void __launch_bounds__(BWD_THREADS)
 render_bwd_kernel(const uint2* __restrict__ ranges, const char* __restrict__ binning_base,
-                  const uint32_t* __restrict__ hdr, int W, int H, int ED,
+                  const uint32_t* __restrict__ hdr, int W, int H, int ED, int band0,
                   const float* __restrict__ bg_color, const float* __restrict__ rec,
                   const float* __restrict__ extras, const float* __restrict__ accum_alphas,
                   const uint32_t* __restrict__ n_contrib, const float* __restrict__ dL_dpixels,
@@ -98,9 +98,10 @@ render_bwd_kernel(const uint2* __restrict__ ranges, const char* __restrict__ bin
 
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int tiles_x = (W + SFGS_TILE - 1) / SFGS_TILE;
-  const int tile = blockIdx.y * tiles_x + blockIdx.x;
+  const int tile_y = blockIdx.y + band0;
+  const int tile = tile_y * tiles_x + blockIdx.x;
   const int px = blockIdx.x * SFGS_TILE + (wid & 1) * 8 + (lane & 7);
-  const int py = blockIdx.y * SFGS_TILE + (wid >> 1) * 4 + (lane >> 3);
+  const int py = tile_y * SFGS_TILE + (wid >> 1) * 4 + (lane >> 3);
   const bool inside = px < W && py < H;
   const uint32_t pix_id = (uint32_t)W * py + px;
   const float pixfx = (float)px, pixfy = (float)py;
@@ -280,17 +281,20 @@ render_bwd_kernel(const uint2* __restrict__ ranges, const char* __restrict__ bin
 
 void sfgs_launch_render_bwd(const sfgs_backward_args* a, const GeomLayout& g, const ImageLayout& im,
                             const BinningLayout& b, float* acc, cudaStream_t st) {
-  dim3 grid(im.tiles_x, im.tiles_y, 1);
+  const int band0 = a->tile_row_end > a->tile_row_begin ? a->tile_row_begin : 0;
+  const int band1 = a->tile_row_end > a->tile_row_begin ? (a->tile_row_end < im.tiles_y ? a->tile_row_end : im.tiles_y) : im.tiles_y;
+  if (band1 <= band0) return;
+  dim3 grid(im.tiles_x, band1 - band0, 1);
   SFGS_COUNT_LAUNCH();
   if (a->ED > 0)
     render_bwd_kernel<true><<<grid, BWD_THREADS, 0, st>>>(
-        im.ranges, (const char*)b.point_list, im.hdr, a->width, a->height, a->ED, a->background, g.rec, a->extra_attrs,
+        im.ranges, (const char*)b.point_list, im.hdr, a->width, a->height, a->ED, band0, a->background, g.rec, a->extra_attrs,
         a->accum_alphas,
         im.n_contrib, a->dL_dpix, a->dL_dpix_depth, a->dL_dpix_norm, a->dL_dpix_alpha, a->dL_dpix_extra, acc,
         a->dL_dextra);
   else
     render_bwd_kernel<false><<<grid, BWD_THREADS, 0, st>>>(
-        im.ranges, (const char*)b.point_list, im.hdr, a->width, a->height, 0, a->background, g.rec, nullptr,
+        im.ranges, (const char*)b.point_list, im.hdr, a->width, a->height, 0, band0, a->background, g.rec, nullptr,
         a->accum_alphas,
         im.n_contrib, a->dL_dpix, a->dL_dpix_depth, a->dL_dpix_norm, a->dL_dpix_alpha, nullptr, acc, nullptr);
 }

@@ -34,6 +34,7 @@ template <bool HAS_EXTRA>
 __global__ void __launch_bounds__(FWD_THREADS)
 render_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list,
                   const unsigned char* __restrict__ inst_mask, const uint32_t* __restrict__ hdr, int W, int H, int ED,
+                  int band0,
                   const float* __restrict__ rec, const float* __restrict__ extras,
                   const float* __restrict__ bg_color, float* __restrict__ out_color,
                   float* __restrict__ out_depth, float* __restrict__ out_norm, float* __restrict__ out_alpha,
@@ -46,10 +47,11 @@ render_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
 
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int tiles_x = (W + SFGS_TILE - 1) / SFGS_TILE;
-  const int tile = blockIdx.y * tiles_x + blockIdx.x;
+  const int tile_y = blockIdx.y + band0;
+  const int tile = tile_y * tiles_x + blockIdx.x;
   // warp w covers the 8x4 block (w%2, w/2) of the tile, lane -> (lane%8, lane/8)
   const int px = blockIdx.x * SFGS_TILE + (wid & 1) * 8 + (lane & 7);
-  const int py = blockIdx.y * SFGS_TILE + (wid >> 1) * 4 + (lane >> 3);
+  const int py = tile_y * SFGS_TILE + (wid >> 1) * 4 + (lane >> 3);
   const bool inside = px < W && py < H;
   const uint32_t pix_id = (uint32_t)W * py + px;
   const float pixfx = (float)px, pixfy = (float)py;
@@ -152,15 +154,18 @@ render_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
 
 void sfgs_launch_render_fwd(const sfgs_forward_args* a, const GeomLayout& g, const ImageLayout& im,
                             const BinningLayout& b, cudaStream_t st) {
-  dim3 grid(im.tiles_x, im.tiles_y, 1);
+  const int band0 = a->tile_row_end > a->tile_row_begin ? a->tile_row_begin : 0;
+  const int band1 = a->tile_row_end > a->tile_row_begin ? (a->tile_row_end < im.tiles_y ? a->tile_row_end : im.tiles_y) : im.tiles_y;
+  if (band1 <= band0) return;
+  dim3 grid(im.tiles_x, band1 - band0, 1);
   SFGS_COUNT_LAUNCH();
   if (a->ED > 0)
-    render_fwd_kernel<true><<<grid, FWD_THREADS, 0, st>>>(im.ranges, b.point_list, b.inst_mask, im.hdr, a->width, a->height, a->ED,
+    render_fwd_kernel<true><<<grid, FWD_THREADS, 0, st>>>(im.ranges, b.point_list, b.inst_mask, im.hdr, a->width, a->height, a->ED, band0,
                                                          g.rec, a->extra_attrs, a->background, a->out_color,
                                                          a->out_depth, a->out_norm, a->out_alpha, a->out_extra,
                                                          im.n_contrib);
   else
-    render_fwd_kernel<false><<<grid, FWD_THREADS, 0, st>>>(im.ranges, b.point_list, b.inst_mask, im.hdr, a->width, a->height, 0,
+    render_fwd_kernel<false><<<grid, FWD_THREADS, 0, st>>>(im.ranges, b.point_list, b.inst_mask, im.hdr, a->width, a->height, 0, band0,
                                                           g.rec, nullptr, a->background, a->out_color, a->out_depth,
                                                           a->out_norm, a->out_alpha, nullptr, im.n_contrib);
 }

@@ -1,0 +1,170 @@
+"""Screen-space (tile-row) sharding of ONE frame across ranks — SURVEY.md §8e, BASELINE.json configs[3].
+
+Nothing like this exists in the reference (its only multi-GPU mode is one scene per process,
+scripts/run_jax.py:52-87).  Design:
+
+* every rank holds the whole scene (or at least every Gaussian that can reach its band);
+* rank g owns a contiguous band of tile rows [cuts[g], cuts[g+1]) chosen so that the number of tile
+  instances per band is balanced (`partition_rows` on the per-row histogram of a previous frame);
+* forward: each rank runs the normal pipeline restricted to its band (`tile_rows=` of
+  sfgs.rasterizer.rasterize_gaussians), then ONE all_gather of the 8 image planes of the bands
+  (padded to the tallest band) assembles the frame on every rank;
+* backward: each rank back-propagates its band's pixels; per-Gaussian gradients are partial sums over
+  bands, combined with ONE all_reduce(sum) (replicated parameters).
+
+The host logic (partitioning, padded gather/assembly, reduction) is backend-agnostic and covered by
+world-size-2 gloo tests on CPU tensors; on B200s the backend is NCCL over NVLink/NVSwitch.
+"""
+from __future__ import annotations
+
+from typing import List, Sequence
+
+import torch
+import torch.distributed as dist
+
+TILE = 16
+
+
+def tile_rows(height: int) -> int:
+    return (height + TILE - 1) // TILE
+
+
+def partition_rows(row_weights: Sequence[float], world: int) -> List[int]:
+    """Cut `len(row_weights)` tile rows into `world` contiguous bands of (nearly) equal total weight.
+    Returns world+1 monotone cut positions, cuts[0] = 0, cuts[-1] = n_rows; every band gets >= 1 row when
+    n_rows >= world.  Deterministic: every rank computes the same cuts from the same histogram."""
+    n = len(row_weights)
+    if world <= 0:
+        raise ValueError("world must be positive")
+    w = [max(float(x), 0.0) + 1e-9 for x in row_weights]
+    total = sum(w)
+    cuts = [0]
+    acc, r = 0.0, 0
+    for g in range(1, world):
+        target = total * g / world
+        while r < n and acc + w[r] * 0.5 < target:
+            acc += w[r]
+            r += 1
+        lo = cuts[-1] + 1 if n >= world else cuts[-1]          # at least one row per band when possible
+        hi = n - (world - g) if n >= world else n
+        cuts.append(min(max(r, lo), max(hi, lo)) if n >= world else min(r, n))
+        # keep the running sum consistent with the cut actually taken
+        acc = sum(w[:cuts[-1]])
+        r = cuts[-1]
+    cuts.append(n)
+    return cuts
+
+
+def band_pixel_rows(cuts: Sequence[int], rank: int, height: int):
+    y0 = min(cuts[rank] * TILE, height)
+    y1 = min(cuts[rank + 1] * TILE, height)
+    return y0, y1
+
+
+def gather_bands(local_planes: torch.Tensor, cuts: Sequence[int], height: int, group=None) -> torch.Tensor:
+    """local_planes: [C, H, W] with only this rank's band rows valid. Returns the assembled [C, H, W].
+    One all_gather of bands padded to the tallest band (bands differ in height after balancing)."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    C, H, W = local_planes.shape
+    assert H == height
+    heights = [band_pixel_rows(cuts, g, height)[1] - band_pixel_rows(cuts, g, height)[0] for g in range(world)]
+    hmax = max(max(heights), 1)
+    y0, y1 = band_pixel_rows(cuts, rank, height)
+    send = torch.zeros((C, hmax, W), dtype=local_planes.dtype, device=local_planes.device)
+    send[:, : y1 - y0] = local_planes[:, y0:y1]
+    recv = torch.empty((world, C, hmax, W), dtype=local_planes.dtype, device=local_planes.device)
+    dist.all_gather_into_tensor(recv.view(-1), send.view(-1), group=group)
+    out = torch.empty_like(local_planes)
+    for g in range(world):
+        a, b = band_pixel_rows(cuts, g, height)
+        out[:, a:b] = recv[g, :, : b - a]
+    return out
+
+
+def reduce_gradients(grads: Sequence[torch.Tensor], group=None) -> None:
+    """Sum the per-band partial per-Gaussian gradients over ranks, in place, with one flat all_reduce."""
+    flat = torch.cat([g.reshape(-1) for g in grads])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    off = 0
+    for g in grads:
+        n = g.numel()
+        g.copy_(flat[off:off + n].view_as(g))
+        off += n
+
+
+def row_histogram(ranges: torch.Tensor, tiles_x: int) -> List[int]:
+    """Instances per tile row from the image buffer's `ranges` [tiles,2]."""
+    cnt = (ranges[:, 1] - ranges[:, 0]).long().view(-1, tiles_x).sum(1)
+    return [int(v) for v in cnt.tolist()]
+
+
+# ----------------------------------------------------------------------------- bench leg (NCCL, one frame sharded)
+def bench_tilerows(args, rank, world, dev, steps, warmup, metric):
+    import json
+
+    import numpy as np
+
+    from . import rasterizer as R
+    from . import synthetic as S
+    scene = S.city_scene(args.P, seed=0, sh_degree=3)
+    cam = S.jax004_camera(1920, 1080)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)  # noqa: E731
+    d = dict(means3D=t(scene.means3D), scales=t(scene.scales), rotations=t(scene.rotations),
+             opacities=t(scene.opacities), shs=t(scene.shs), view=t(cam.viewmatrix), proj=t(cam.projmatrix),
+             campos=t(cam.campos), bg=torch.zeros(3, device=dev))
+    cot = [t(c) for c in S.cotangents(cam.width, cam.height, seed=1)]
+    e = torch.empty(0, device=dev)
+    H, W = cam.height, cam.width
+    rows, tiles_x = tile_rows(H), (W + TILE - 1) // TILE
+
+    def fwd(band):
+        return R.rasterize_gaussians(d["bg"], d["means3D"], e, d["opacities"], d["scales"], d["rotations"], 1.0, e, e,
+                                     e, 0, d["view"], d["proj"], cam.tanfovx, cam.tanfovy, 0.1, H, W, d["shs"], 3,
+                                     d["campos"], False, False, tile_rows=band)
+
+    # setup (untimed): one full-frame pass for the per-row histogram -> balanced cuts, identical on every rank
+    f0 = fwd(None)
+    from . import native as N
+    import ctypes as C
+    iv = N.ImageView()
+    N.check(N.lib().sfgs_image_layout(f0[9].data_ptr(), W, H, C.byref(iv)), "image_layout")
+    off = iv.ranges - f0[9].data_ptr()
+    ranges = f0[9][off:off + rows * tiles_x * 8].view(torch.int32).view(-1, 2)
+    cuts = partition_rows(row_histogram(ranges, tiles_x), world)
+    band = (cuts[rank], cuts[rank + 1])
+
+    def step():
+        f = fwd(band)
+        planes = torch.cat([f[1], f[2], f[4], f[3]], 0)            # colour, depth, alpha, normal: 8 planes
+        full = gather_bands(planes, cuts, H)
+        g = R.rasterize_gaussians_backward(d["bg"], d["means3D"], f[5], e, d["scales"], d["rotations"], e, 1.0, e, e,
+                                           d["view"], d["proj"], cam.tanfovx, cam.tanfovy, 0.1, cot[0], cot[1], cot[2],
+                                           cot[3], e, d["shs"], 3, d["campos"], f[7], f[0], f[8], f[9], f[4], False,
+                                           tile_rows=band)
+        reduce_gradients([g[3], g[0], g[6], g[2], g[7], g[8]])
+        return full
+
+    for _ in range(warmup):
+        step()
+    dist.barrier()
+    torch.cuda.synchronize(dev)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(steps):
+        step()
+    b.record()
+    dist.barrier()
+    torch.cuda.synchronize(dev)
+    ms = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        total = float(ms.item())
+        print(json.dumps({"metric": metric, "value": round(steps * H * W / (total / 1e3) / 1e6, 2), "unit": "Mpix/s",
+                          "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": round(total / steps, 4),
+                          "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+                          "data": "synthetic",
+                          "config": {"workload": "one 1920x1080 frame of the 1M-Gaussian scene sharded by tile rows",
+                                     "parallelism": f"tilerows x{world}: image all_gather + gradient all_reduce (NCCL)",
+                                     "cuts": cuts, "l2": "not flushed (collectives in the loop)"}}))
+    dist.destroy_process_group()

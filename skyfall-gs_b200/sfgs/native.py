@@ -36,6 +36,7 @@ class ForwardArgs(C.Structure):
         ("out_color", c_float_p), ("out_depth", c_float_p), ("out_norm", c_float_p),
         ("out_alpha", c_float_p), ("out_extra", c_float_p), ("radii", c_int_p),
         ("debug", C.c_int), ("stream", C.c_void_p), ("capacity_hint", C.c_longlong),
+        ("tile_row_begin", C.c_int), ("tile_row_end", C.c_int),
     ]
 
 
@@ -60,6 +61,7 @@ class BackwardArgs(C.Structure):
         ("dL_dscale", c_float_p), ("dL_drot", c_float_p), ("dL_dextra", c_float_p),
         ("scratch_alloc", ALLOC_FN), ("scratch_user", C.c_void_p),
         ("debug", C.c_int), ("stream", C.c_void_p),
+        ("tile_row_begin", C.c_int), ("tile_row_end", C.c_int),
     ]
 
 

@@ -53,7 +53,7 @@ class _Arena:
 def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations, scale_modifier,
                         cov3Ds_precomp, norm3Ds_precomp, extra_attrs, attr_degree, viewmatrix, projmatrix,
                         tan_fovx, tan_fovy, kernel_size, image_height, image_width, sh, degree, campos,
-                        prefiltered, debug, capacity_hint=0):
+                        prefiltered, debug, capacity_hint=0, tile_rows=None):
     if means3D.ndim != 2 or means3D.shape[1] != 3:
         raise RuntimeError("means3D must have dimensions (num_points, 3)")
     L = N.lib()
@@ -107,6 +107,8 @@ def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations,
         a.debug = int(bool(debug))
         a.stream = torch.cuda.current_stream(dev).cuda_stream
         a.capacity_hint = int(capacity_hint)
+        if tile_rows is not None:
+            a.tile_row_begin, a.tile_row_end = int(tile_rows[0]), int(tile_rows[1])
         rendered = N.check(L.sfgs_rasterize_forward(C.byref(a)), "sfgs_rasterize_forward")
     return (rendered, out_color, out_depth, out_norm, out_alpha, radii, out_extra,
             geom.tensor, binning.tensor, img.tensor)
@@ -116,7 +118,7 @@ def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rot
                                  cov3Ds_precomp, norm3Ds_precomp, viewmatrix, projmatrix, tan_fovx, tan_fovy,
                                  kernel_size, dL_dout_color, dL_dout_depth, dL_dout_norm, dL_dout_alpha,
                                  dL_dout_extra, sh, degree, campos, geomBuffer, R, binningBuffer, imageBuffer,
-                                 out_alpha, debug):
+                                 out_alpha, debug, tile_rows=None):
     L = N.lib()
     P = int(means3D.shape[0])
     H, W = int(dL_dout_color.shape[1]), int(dL_dout_color.shape[2])
@@ -184,6 +186,8 @@ def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rot
         a.scratch_alloc = scratch.cb
         a.debug = int(bool(debug))
         a.stream = torch.cuda.current_stream(dev).cuda_stream
+        if tile_rows is not None:
+            a.tile_row_begin, a.tile_row_end = int(tile_rows[0]), int(tile_rows[1])
         N.check(L.sfgs_rasterize_backward(C.byref(a)), "sfgs_rasterize_backward")
     return (outs["means2D"], outs["colors"], outs["opacity"], outs["means3D"], outs["cov3D"], outs["norm3D"],
             dL_dsh, outs["scales"], outs["rot"], dL_dextra)

@@ -71,4 +71,5 @@ def test_dist_cuda2_matches_bruteforce_and_reference(cuda_device):
     from oracle import ref_cuda
     if ref_cuda.available():
         pts = torch.from_numpy(clouds["uniform"].astype(np.float32)).to(dev)
-        assert torch.equal(distCUDA2(pts), ref_cuda.knn(pts))   # same float expression, same 3-NN set
+        # same 3-NN set; the squared distance may contract differently (1 ulp)
+        assert torch.allclose(distCUDA2(pts), ref_cuda.knn(pts), rtol=1e-6, atol=0)

@@ -1,0 +1,72 @@
+"""Host logic of the tile-row sharding on CPU: partitioning, and world-size-2 gloo runs of the padded band
+gather and the flat gradient reduction (no GPU needed)."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from sfgs import multigpu as MG
+
+
+def test_partition_rows_balanced_and_total():
+    w = [0, 0, 5, 50, 80, 80, 60, 10, 1, 0, 0, 0]
+    for world in (1, 2, 3, 4, 8):
+        cuts = MG.partition_rows(w, world)
+        assert cuts[0] == 0 and cuts[-1] == len(w) and len(cuts) == world + 1
+        assert all(b > a for a, b in zip(cuts, cuts[1:]))          # every band non-empty (12 rows >= world)
+    cuts = MG.partition_rows(w, 2)
+    left, right = sum(w[:cuts[1]]), sum(w[cuts[1]:])
+    assert abs(left - right) <= max(w)
+    # fewer rows than ranks: still monotone, covers everything
+    cuts = MG.partition_rows([3, 1], 4)
+    assert cuts[0] == 0 and cuts[-1] == 2 and all(b >= a for a, b in zip(cuts, cuts[1:]))
+    # uniform weights -> equal split
+    assert MG.partition_rows([1] * 68, 4) == [0, 17, 34, 51, 68]
+    assert MG.tile_rows(1080) == 68 and MG.band_pixel_rows([0, 34, 68], 1, 1080) == (544, 1080)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        H, W, C = 100, 37, 8                          # 7 tile rows, last one partial
+        cuts = [0, 5, 7]                              # unequal bands: 80 and 20 pixel rows
+        truth = torch.arange(C * H * W, dtype=torch.float32).view(C, H, W)
+        local = torch.full((C, H, W), float("nan"))
+        y0, y1 = MG.band_pixel_rows(cuts, rank, H)
+        local[:, y0:y1] = truth[:, y0:y1]
+        full = MG.gather_bands(local, cuts, H)
+        ok_gather = bool(torch.equal(full, truth))
+        g1 = torch.full((5, 3), float(rank + 1))
+        g2 = torch.full((5,), 10.0 * (rank + 1))
+        MG.reduce_gradients([g1, g2])
+        ok_reduce = bool(torch.all(g1 == 3.0)) and bool(torch.all(g2 == 30.0))
+        out.put((rank, ok_gather, ok_reduce))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gather_and_reduce_world2_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(r[0] for r in res) == [0, 1]
+    assert all(r[1] for r in res), "padded band all_gather did not reassemble the frame"
+    assert all(r[2] for r in res), "flat gradient all_reduce mismatch"
