@@ -46,7 +46,8 @@ def test_oracle_matches_reference_cuda(name):
     # ---- blended images: glibc expf vs CUDA expf differ by <= 2 ulp; a borderline alpha/T test may flip a pixel
     for k in ("color", "depth", "norm", "alpha"):
         d = np.abs(f[k] - g[k])
-        assert np.quantile(d, 0.999) <= 1e-5 and d.max() <= 5e-3, (k, d.max())
+        scale = max(1.0, float(np.abs(g[k]).max()))       # depth is un-normalised (hundreds of scene units)
+        assert np.quantile(d, 0.999) <= 1e-5 * scale and d.max() <= 5e-3 * scale, (k, d.max())
     assert (f["n_contrib"] != g["int_n_contrib"].astype(np.uint32)).mean() < 1e-3
     # ---- gradients: within the reference's own atomic-order noise
     gb = O.backward(f, *kw["cot"])
