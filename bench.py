@@ -226,16 +226,23 @@ class E2EOurs:
         self.sub = torch.zeros(1, device=dev)
         self.h2d_bytes = self.h_cam.numel() * 4 + self.h_gt.numel() * 4
         self.d2h_bytes = 4
+        self.copy_stream = torch.cuda.Stream(dev)
 
     def step(self):
         cam = self.cam
+        cur = torch.cuda.current_stream(self.dev)
         dcam = self.h_cam.to(self.dev, non_blocking=True)
-        gt = self.h_gt.to(self.dev, non_blocking=True)
+        # the target image is only needed by the loss: copy it on a side stream while the forward runs
+        self.copy_stream.wait_stream(cur)
+        with torch.cuda.stream(self.copy_stream):
+            gt = self.h_gt.to(self.dev, non_blocking=True)
         rs = self.GRS(cam.height, cam.width, cam.tanfovx, cam.tanfovy, 0.1, self.sub, self.bg, 1.0,
                       dcam[0:16].view(4, 4), dcam[16:32].view(4, 4), SH_DEGREE, dcam[32:35], False, False)
         means3D, opac, shs, scales, rots = self.params
         color, depth, norm, alpha, radii, _ = self.GR(rs)(means3D, self.means2D, opac, shs=shs, scales=scales,
                                                           rotations=rots)
+        cur.wait_stream(self.copy_stream)
+        gt.record_stream(cur)
         loss = (color - gt).abs().mean() + 0.01 * depth.mean() + 0.01 * (1 - alpha).mean() + 0.01 * norm.mean()
         for p in self.params:
             p.grad = None
@@ -257,15 +264,21 @@ class E2ERef:
         self.h_loss = torch.zeros(1).pin_memory()
         self.h2d_bytes = self.h_cam.numel() * 4 + self.h_gt.numel() * 4
         self.d2h_bytes = 4
+        self.copy_stream = torch.cuda.Stream(dev)
 
     def step(self):
         from oracle import ref_cuda
         d, cam, e = self.d, self.cam, self.d["empty"]
+        cur = torch.cuda.current_stream(self.dev)
         dcam = self.h_cam.to(self.dev, non_blocking=True)
-        gt = self.h_gt.to(self.dev, non_blocking=True)
+        self.copy_stream.wait_stream(cur)
+        with torch.cuda.stream(self.copy_stream):
+            gt = self.h_gt.to(self.dev, non_blocking=True)
         view, proj, campos = dcam[0:16].view(4, 4), dcam[16:32].view(4, 4), dcam[32:35]
         f = ref_cuda.forward(d["bg"], d["means3D"], e, d["opacities"], d["scales"], d["rotations"], 1.0, e, e, e, view,
                              proj, cam.tanfovx, cam.tanfovy, 0.1, cam.height, cam.width, d["shs"], SH_DEGREE, campos)
+        cur.wait_stream(self.copy_stream)
+        gt.record_stream(cur)
         n = float(cam.height * cam.width)
         norm_raw = f["norm"].detach().requires_grad_(True)
         norm = torch.nn.functional.normalize(norm_raw, p=2, dim=0)

@@ -164,6 +164,7 @@ int sfgs_rasterize_forward(const sfgs_forward_args* a) {
     if (!a->cov3D_precomp && (!a->scales || !a->rotations)) return fail(SFGS_E_BADARG, "forward: need scales+rotations or cov3D_precomp");
     if (!a->norm3D_precomp && (!a->scales || !a->rotations)) return fail(SFGS_E_BADARG, "forward: need scales+rotations or norm3D_precomp");
     if (a->ED > 0 && (!a->extra_attrs || !a->out_extra)) return fail(SFGS_E_BADARG, "forward: extra attrs missing");
+    if (a->rotations && (reinterpret_cast<uintptr_t>(a->rotations) & 15)) return fail(SFGS_E_BADARG, "forward: rotations must be 16-byte aligned");
   }
   cudaStream_t st = (cudaStream_t)a->stream;
   const bool debug = a->debug != 0;
@@ -257,6 +258,7 @@ int sfgs_rasterize_backward(const sfgs_backward_args* a) {
   if (a->M > 0 && a->shs && !a->dL_dsh) return fail(SFGS_E_BADARG, "backward: dL_dsh missing");
   if (a->ED > 0 && (!a->dL_dextra || !a->dL_dpix_extra || !a->extra_attrs)) return fail(SFGS_E_BADARG, "backward: extra attrs missing");
   if (!a->scratch_alloc) return fail(SFGS_E_BADARG, "backward: null scratch allocator");
+  if (a->rotations && (reinterpret_cast<uintptr_t>(a->rotations) & 15)) return fail(SFGS_E_BADARG, "backward: rotations must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)a->stream;
   const bool debug = a->debug != 0;
   const int P = a->P;

@@ -87,19 +87,26 @@ scatter_keys_kernel(const uint4* __restrict__ tmp, const uint2* __restrict__ ran
 // bitonic network on 64-bit (depth_bits << 32 | id) keys padded with ~0.
 template <int THREADS>
 __device__ __forceinline__ void bitonic_smem(uint64_t* s, int n2) {
+  // Compare-exchange i of a stage touches lo = ((i & ~(j-1)) << 1) | (i & (j-1)) and hi = lo | j.  For j <= 32 the
+  // 32 exchanges of one warp stay inside one aligned 64-key block, so consecutive stages with j <= 32 only need
+  // __syncwarp(); block-wide barriers remain only for the strides j >= 64 (6 instead of 45 barriers at n2 = 512).
+  const int half = n2 >> 1;
   for (int k = 2; k <= n2; k <<= 1) {
     for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int i = threadIdx.x; i < (n2 >> 1); i += THREADS) {
-        // i-th compare-exchange of this stage: lower index has bit j clear
+      for (int i = threadIdx.x; i < half; i += THREADS) {
         const int lo = ((i & ~(j - 1)) << 1) | (i & (j - 1));
         const int hi = lo | j;
         const uint64_t a = s[lo], b = s[hi];
         const bool up = ((lo & k) == 0);
         if ((a > b) == up) { s[lo] = b; s[hi] = a; }
       }
-      __syncthreads();
+      // the next stage has stride j/2: it is warp-local iff j/2 <= 32, and this stage's writes came from the
+      // same warp iff j <= 32
+      if (j > 32 || (j == 1 && (k << 1) > 64 && k < n2)) __syncthreads();
+      else __syncwarp();
     }
   }
+  __syncthreads();
 }
 
 // stable LSD radix sort of n 64-bit keys, 8 bits per pass, one CTA of 256 threads, global ping-pong

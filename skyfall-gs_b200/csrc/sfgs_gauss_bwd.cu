@@ -33,7 +33,7 @@ __device__ __forceinline__ float3 dnormvdv3(float3 v, float3 dv) {
 }
 
 template <bool WRITE_SH>
-__global__ void __launch_bounds__(GB_THREADS)
+__global__ void __launch_bounds__(GB_THREADS, 5)
 gauss_bwd_kernel(int P, int D, int M, const float* __restrict__ means3D, const int* __restrict__ radii,
                  const float* __restrict__ shs, const unsigned char* __restrict__ clamped,
                  const float* __restrict__ scales, const float* __restrict__ rotations, float scale_modifier,
@@ -45,8 +45,9 @@ gauss_bwd_kernel(int P, int D, int M, const float* __restrict__ means3D, const i
                  float* __restrict__ dL_dcolor, float* __restrict__ dL_ddepth, float* __restrict__ dL_dmean3D,
                  float* __restrict__ dL_dcov3D, float* __restrict__ dL_dnorm3D, float* __restrict__ dL_dsh,
                  float* __restrict__ dL_dscale, float* __restrict__ dL_drot) {
-  const int idx = blockIdx.x * GB_THREADS + threadIdx.x;
-  if (idx >= P) return;
+  const int idx_raw = blockIdx.x * GB_THREADS + threadIdx.x;
+  const bool in_range = idx_raw < P;
+  const int idx = in_range ? idx_raw : P - 1;     // out-of-range threads idle through the math, join the block-wide store
   const size_t i = (size_t)idx;
 
   float o_mean2D[3] = {0, 0, 0}, o_conic[4] = {0, 0, 0, 0}, o_opac = 0, o_color[3] = {0, 0, 0}, o_depth = 0;
@@ -56,7 +57,7 @@ gauss_bwd_kernel(int P, int D, int M, const float* __restrict__ means3D, const i
 #pragma unroll
   for (int k = 0; k < 16; k++) dsh_scale[k] = 0.f;
   float dL_dRGB[3] = {0, 0, 0};
-  const bool visible = radii[idx] > 0;
+  const bool visible = in_range && radii[idx] > 0;
 
   if (visible) {
     const float4* a4 = reinterpret_cast<const float4*>(acc + i * 16);
@@ -315,31 +316,80 @@ gauss_bwd_kernel(int P, int D, int M, const float* __restrict__ means3D, const i
     }
   }
 
-  // ---------------- write every output exactly once ----------------
-  dL_dmean2D[3 * i] = o_mean2D[0]; dL_dmean2D[3 * i + 1] = o_mean2D[1]; dL_dmean2D[3 * i + 2] = o_mean2D[2];
-  *reinterpret_cast<float4*>(dL_dconic + 4 * i) = make_float4(o_conic[0], o_conic[1], o_conic[2], o_conic[3]);
-  dL_dopacity[i] = o_opac;
-  dL_dcolor[3 * i] = o_color[0]; dL_dcolor[3 * i + 1] = o_color[1]; dL_dcolor[3 * i + 2] = o_color[2];
-  dL_ddepth[i] = o_depth;
-  dL_dmean3D[3 * i] = o_mean[0]; dL_dmean3D[3 * i + 1] = o_mean[1]; dL_dmean3D[3 * i + 2] = o_mean[2];
+  // ---------------- write every output exactly once, coalesced ----------------
+  // Per-thread stores of 3/4/6/48-float rows are strided across the warp (20 sectors per request measured);
+  // stage the block's rows in shared memory and stream each output array out as contiguous 16-byte stores.
+  __shared__ __align__(16) float s_out[GB_THREADS * 31];
+  __shared__ __align__(16) float s_sh[GB_THREADS * 19];
+  const int t = threadIdx.x;
+  float* sp = s_out;
+  // array order and widths: mean2D 3, conic 4, opacity 1, color 3, depth 1, mean3D 3, cov3D 6, norm3D 3, scale 3, rot 4
+  float* s_mean2D = sp; sp += GB_THREADS * 3;
+  float* s_conic = sp; sp += GB_THREADS * 4;
+  float* s_opac = sp; sp += GB_THREADS * 1;
+  float* s_color = sp; sp += GB_THREADS * 3;
+  float* s_depth = sp; sp += GB_THREADS * 1;
+  float* s_mean = sp; sp += GB_THREADS * 3;
+  float* s_cov = sp; sp += GB_THREADS * 6;
+  float* s_norm = sp; sp += GB_THREADS * 3;
+  float* s_scale = sp; sp += GB_THREADS * 3;
+  float* s_rot = sp;
+  s_mean2D[3 * t] = o_mean2D[0]; s_mean2D[3 * t + 1] = o_mean2D[1]; s_mean2D[3 * t + 2] = o_mean2D[2];
+  *reinterpret_cast<float4*>(s_conic + 4 * t) = make_float4(o_conic[0], o_conic[1], o_conic[2], o_conic[3]);
+  s_opac[t] = o_opac;
+  s_color[3 * t] = o_color[0]; s_color[3 * t + 1] = o_color[1]; s_color[3 * t + 2] = o_color[2];
+  s_depth[t] = o_depth;
+  s_mean[3 * t] = o_mean[0]; s_mean[3 * t + 1] = o_mean[1]; s_mean[3 * t + 2] = o_mean[2];
 #pragma unroll
-  for (int k = 0; k < 6; k++) dL_dcov3D[6 * i + k] = o_cov[k];
-  dL_dnorm3D[3 * i] = o_norm[0]; dL_dnorm3D[3 * i + 1] = o_norm[1]; dL_dnorm3D[3 * i + 2] = o_norm[2];
-  dL_dscale[3 * i] = o_scale[0]; dL_dscale[3 * i + 1] = o_scale[1]; dL_dscale[3 * i + 2] = o_scale[2];
-  *reinterpret_cast<float4*>(dL_drot + 4 * i) = make_float4(o_rot[0], o_rot[1], o_rot[2], o_rot[3]);
+  for (int k = 0; k < 6; k++) s_cov[6 * t + k] = o_cov[k];
+  s_norm[3 * t] = o_norm[0]; s_norm[3 * t + 1] = o_norm[1]; s_norm[3 * t + 2] = o_norm[2];
+  s_scale[3 * t] = o_scale[0]; s_scale[3 * t + 1] = o_scale[1]; s_scale[3 * t + 2] = o_scale[2];
+  *reinterpret_cast<float4*>(s_rot + 4 * t) = make_float4(o_rot[0], o_rot[1], o_rot[2], o_rot[3]);
   if (WRITE_SH) {
-    float* out = dL_dsh + i * M * 3;
-    if (M == 16) {
-      float4* o4 = reinterpret_cast<float4*>(out);
-      float buf[48];
 #pragma unroll
-      for (int k = 0; k < 16; k++) { buf[3 * k] = dsh_scale[k] * dL_dRGB[0]; buf[3 * k + 1] = dsh_scale[k] * dL_dRGB[1]; buf[3 * k + 2] = dsh_scale[k] * dL_dRGB[2]; }
+    for (int k = 0; k < 16; k++) s_sh[19 * t + k] = dsh_scale[k];
+    s_sh[19 * t + 16] = dL_dRGB[0]; s_sh[19 * t + 17] = dL_dRGB[1]; s_sh[19 * t + 18] = dL_dRGB[2];
+  }
+  __syncthreads();
+  const size_t base = (size_t)blockIdx.x * GB_THREADS;            // first Gaussian of this block
+  const int nvalid = min(GB_THREADS, P - (int)base);              // Gaussians of this block that exist
+  auto stream_out = [&](const float* src, float* dst, int width) {
+    const int nfl = nvalid * width;                                // floats to write, contiguous in dst
+    float* d = dst + base * width;                                 // 16-byte aligned: base is a multiple of 128
+    const int nv4 = ((reinterpret_cast<uintptr_t>(d) & 15) == 0) ? (nfl >> 2) : 0;   // caller buffers may be unaligned
+    for (int i = t; i < nv4; i += GB_THREADS) reinterpret_cast<float4*>(d)[i] = reinterpret_cast<const float4*>(src)[i];
+    for (int i = (nv4 << 2) + t; i < nfl; i += GB_THREADS) d[i] = src[i];
+  };
+  stream_out(s_mean2D, dL_dmean2D, 3);
+  stream_out(s_conic, dL_dconic, 4);
+  stream_out(s_opac, dL_dopacity, 1);
+  stream_out(s_color, dL_dcolor, 3);
+  stream_out(s_depth, dL_ddepth, 1);
+  stream_out(s_mean, dL_dmean3D, 3);
+  stream_out(s_cov, dL_dcov3D, 6);
+  stream_out(s_norm, dL_dnorm3D, 3);
+  stream_out(s_scale, dL_dscale, 3);
+  stream_out(s_rot, dL_drot, 4);
+  if (WRITE_SH) {
+    // dL_dsh[g][k][ch] = dRGB/dsh_k(g) * dL_dRGB[ch](g); output index i -> g = i / (3M), k = (i % 3M) / 3, ch = i % 3
+    const int row = 3 * M;
+    const int nfl = nvalid * row;
+    float* d = dL_dsh + base * row;
+    if ((row & 3) == 0 && (reinterpret_cast<uintptr_t>(d) & 15) == 0) {
+      for (int i4 = t; i4 < (nfl >> 2); i4 += GB_THREADS) {
+        float v[4];
 #pragma unroll
-      for (int k = 0; k < 12; k++) o4[k] = make_float4(buf[4 * k], buf[4 * k + 1], buf[4 * k + 2], buf[4 * k + 3]);
+        for (int c = 0; c < 4; c++) {
+          const int i = 4 * i4 + c;
+          const int gl = i / row, r = i - gl * row, k = r / 3, ch = r - 3 * k;
+          v[c] = (k < 16 ? s_sh[19 * gl + k] : 0.f) * s_sh[19 * gl + 16 + ch];
+        }
+        reinterpret_cast<float4*>(d)[i4] = make_float4(v[0], v[1], v[2], v[3]);
+      }
     } else {
-      for (int k = 0; k < M; k++) {
-        const float sc = k < 16 ? dsh_scale[k] : 0.f;
-        out[3 * k] = sc * dL_dRGB[0]; out[3 * k + 1] = sc * dL_dRGB[1]; out[3 * k + 2] = sc * dL_dRGB[2];
+      for (int i = t; i < nfl; i += GB_THREADS) {
+        const int gl = i / row, r = i - gl * row, k = r / 3, ch = r - 3 * k;
+        d[i] = (k < 16 ? s_sh[19 * gl + k] : 0.f) * s_sh[19 * gl + 16 + ch];
       }
     }
   }

@@ -248,7 +248,7 @@ preprocess_kernel(int P, int D, int M,
         unsigned cmask = 0;
         if (colors_precomp == nullptr) {
           const float* shp = shs + (size_t)idx * M * 3;
-          if (M == 16) {
+          if (M == 16 && (reinterpret_cast<uintptr_t>(shs) & 15) == 0) {
             // 192 contiguous, 16-byte aligned bytes per Gaussian: twelve 128-bit loads instead of 48 scalar ones
             float shl[48];
             const float4* s4 = reinterpret_cast<const float4*>(shp);

@@ -1,25 +1,47 @@
 // sfgs_render_bwd.cu — adjoint of the alpha compositing, one CTA per 16x16 tile.
 //
-// Replaces BACKWARD::render / renderCUDA (RAST/cuda_rasterizer/backward.cu:509-754).
-// The reference issues >= 14 global float atomicAdd per (pixel, Gaussian) pair.
-// Here every warp (an 8x4 pixel block) reduces its 14 partial gradients with a
-// 16-shuffle butterfly, the 8 warps of a tile are combined in a fixed order
-// through shared-memory slots, and one 16-byte vector reduction per (tile,
-// Gaussian, quarter) reaches global memory: ~1000x fewer global atomics, and
-// everything inside a tile is deterministic.
+// Replaces BACKWARD::render / renderCUDA (RAST/cuda_rasterizer/backward.cu:509-754), which issues >= 14
+// global float atomicAdd per (pixel, Gaussian) pair.
 //
-// The per-pixel recursion uses the scalar form of the reference's accumulators:
-//   dL/dalpha_j = T_j * ( g_j - A_j ),  g_j = <dL/dpix, attr_j>,
-//   A_j = alpha_{j+1} g_{j+1} + (1 - alpha_{j+1}) A_{j+1}
-// which is the channel-sum of accum_rec/accum_red/accum_ren/accum_rea
-// (backward.cu:660-711) and needs 3 registers instead of 16.
+// Structure (each warp owns an 8x4 pixel block and walks, back to front, only the records whose reach mask
+// touches its block — see sfgs_common.cuh):
+//
+//   phase 1, pixel-parallel (lane = pixel): the per-pixel recursion.  The reference's eight per-channel
+//     accumulators collapse into the scalar form
+//         dL/dalpha_j = T_j (g_j - A_j),  g_j = <dL/dpix, attr_j>,  A_j = a_{j+1} g_{j+1} + (1 - a_{j+1}) A_{j+1}
+//     (the channel-sum of accum_rec/accum_red/accum_ren/accum_rea, backward.cu:660-711).  Per pair only two
+//     numbers leave the lane:  w = alpha*T  and  h = G * dL/dalpha ; they are parked in a per-warp
+//     shared-memory tile [pixel][record].
+//   phase 2, record-parallel (lane = record of a 16-record chunk x half of the block's pixels): all 14
+//     per-Gaussian sums are linear in (w, h):
+//         sum w*dL/dpix_c (7 channels),  sum h*{1, dx, dy, dx^2, dx dy, dy^2},  sum |..| for the abs-gradient,
+//     so each lane streams down its record's column of the tile accumulating in registers — no cross-lane
+//     reduction except one 16-lane exchange between the two pixel halves.  This replaces the 16-shuffle
+//     butterfly per (warp, record) of the first version of this kernel (~45 % fewer issued instructions).
+//   combine: the 8 warps' partial sums meet in shared-memory slots in a fixed order and one
+//     red.global.add.v4.f32 per (tile, Gaussian, quarter) reaches HBM: ~1000x fewer global atomics than the
+//     reference, deterministic inside a tile.
 #include "sfgs_common.cuh"
 
 namespace {
 
 constexpr int BWD_THREADS = 256;
 constexpr int BWD_WARPS = BWD_THREADS / 32;
-constexpr int BWD_BATCH = 64;
+constexpr int BWD_BATCH = 32;     // records staged per step
+constexpr int CH = 16;            // records per phase-2 chunk
+constexpr int PIXF = 12;          // floats per pixel-table row: dLc[3], dLd, dLn[3], px, py, pad[3]
+
+struct BwdSmem {
+  float4 rec[2][BWD_BATCH][4];                 // 4 KB   staged blend records
+  uint32_t id[2][BWD_BATCH];
+  uint32_t bits[2][BWD_WARPS];                 // per block: which staged records can reach it
+  float part[BWD_WARPS][BWD_BATCH][16];        // 16 KB  per-warp partial sums of the current batch
+  uint32_t pmask[BWD_WARPS];                   // which records of the batch each warp wrote
+  uint32_t maxc[BWD_WARPS];
+  float2 wh[BWD_WARPS][32][CH + 1];            // 34 KB  phase-1 -> phase-2 hand-over, [pixel][record], padded
+  float pix[BWD_THREADS][PIXF];                // 12 KB  per-pixel cotangents and coordinates
+  uint32_t chunk_e[BWD_WARPS][CH];             // record index (within the batch) of every chunk slot
+};
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
   const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
@@ -33,48 +55,8 @@ __device__ __forceinline__ void red_add_v4(float* addr, float4 v) {
                : "memory");
 }
 
-// 16 values per lane -> component (lane >> 1) summed over the warp, valid in every lane
-__device__ __forceinline__ float butterfly16(const float v[16], int lane) {
-  float w[8], x[4], y[2], z;
-  {
-    const bool hi = lane & 16;
-#pragma unroll
-    for (int i = 0; i < 8; i++) {
-      const float send = hi ? v[i] : v[i + 8];
-      const float keep = hi ? v[i + 8] : v[i];
-      w[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-    }
-  }
-  {
-    const bool hi = lane & 8;
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-      const float send = hi ? w[i] : w[i + 4];
-      const float keep = hi ? w[i + 4] : w[i];
-      x[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-    }
-  }
-  {
-    const bool hi = lane & 4;
-#pragma unroll
-    for (int i = 0; i < 2; i++) {
-      const float send = hi ? x[i] : x[i + 2];
-      const float keep = hi ? x[i + 2] : x[i];
-      y[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-    }
-  }
-  {
-    const bool hi = lane & 2;
-    const float send = hi ? y[0] : y[1];
-    const float keep = hi ? y[1] : y[0];
-    z = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-  }
-  z += __shfl_xor_sync(0xffffffffu, z, 1);
-  return z;
-}
-
 template <bool HAS_EXTRA>
-__global__ void __launch_bounds__(BWD_THREADS)
+__global__ void __launch_bounds__(BWD_THREADS, 3)
 render_bwd_kernel(const uint2* __restrict__ ranges, const char* __restrict__ binning_base,
                   const uint32_t* __restrict__ hdr, int W, int H, int ED, int band0,
                   const float* __restrict__ bg_color, const float* __restrict__ rec,
@@ -83,12 +65,8 @@ render_bwd_kernel(const uint2* __restrict__ ranges, const char* __restrict__ bin
                   const float* __restrict__ dL_dpixel_depths, const float* __restrict__ dL_dpixel_norms,
                   const float* __restrict__ dL_dpixel_alphas, const float* __restrict__ dL_dpixel_extras,
                   float* __restrict__ acc /* [P,16] zero-initialised */, float* __restrict__ dL_dextras) {
-  __shared__ __align__(16) float4 s_rec[2][BWD_BATCH][4];                 // 8 KB
-  __shared__ uint32_t s_id[2][BWD_BATCH];
-  __shared__ __align__(16) float s_part[BWD_WARPS][BWD_BATCH][16];        // 32 KB
-  __shared__ unsigned long long s_mask[BWD_WARPS];
-  __shared__ uint32_t s_maxc[BWD_WARPS];
-  __shared__ uint32_t s_bits[2][BWD_WARPS][BWD_BATCH / 32];
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  BwdSmem& S = *reinterpret_cast<BwdSmem*>(smem_raw);
 
   // the binning buffer layout depends on the capacity the forward used; it is recorded in the image header
   const unsigned long long cap = ((unsigned long long)hdr[HDR_CAP_HI] << 32) | hdr[HDR_CAP_LO];
@@ -124,6 +102,12 @@ render_bwd_kernel(const uint2* __restrict__ ranges, const char* __restrict__ bin
   }
   float bg_dot = 0;
   bg_dot += bg_color[0] * dLc0; bg_dot += bg_color[1] * dLc1; bg_dot += bg_color[2] * dLc2;
+  {
+    float4* pt = reinterpret_cast<float4*>(&S.pix[tid][0]);
+    pt[0] = make_float4(dLc0, dLc1, dLc2, dLd);
+    pt[1] = make_float4(dLn0, dLn1, dLn2, pixfx);
+    pt[2] = make_float4(pixfy, 0.f, 0.f, 0.f);
+  }
 
   // extra-attribute slow path state (generic fallback, Skyfall-GS never uses it)
   float accum_ree[HAS_EXTRA ? SFGS_MAX_EXTRA : 1];
@@ -138,15 +122,15 @@ render_bwd_kernel(const uint2* __restrict__ ranges, const char* __restrict__ bin
   const float ddelx_dx = 0.5 * W;
   const float ddely_dy = 0.5 * H;
 
-  // entries at list position >= max(last_contributor) over the tile are never used: skip them entirely
+  // records at list position >= max(last_contributor) over the tile are never used: skip them entirely
   uint32_t wmax = last_contributor;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) wmax = max(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
-  if (lane == 0) s_maxc[wid] = wmax;
+  if (lane == 0) S.maxc[wid] = wmax;
   __syncthreads();
   uint32_t bmax = 0;
 #pragma unroll
-  for (int w = 0; w < BWD_WARPS; w++) bmax = max(bmax, s_maxc[w]);
+  for (int w = 0; w < BWD_WARPS; w++) bmax = max(bmax, S.maxc[w]);
   const int used = min((int)bmax, total);   // positions [0, used) matter
   if (used == 0) return;
   const int nbatches = (used + BWD_BATCH - 1) / BWD_BATCH;
@@ -162,8 +146,8 @@ render_bwd_kernel(const uint2* __restrict__ ranges, const char* __restrict__ bin
           const uint32_t id = point_list[range.x + pos];
           const float* src = rec + (size_t)id * REC_FLOATS;
 #pragma unroll
-          for (int q = 0; q < 4; q++) cp_async16(&s_rec[stage][tid][q], src + q * 4);
-          s_id[stage][tid] = id;
+          for (int q = 0; q < 4; q++) cp_async16(&S.rec[stage][tid][q], src + q * 4);
+          S.id[stage][tid] = id;
         }
       }
     }
@@ -172,33 +156,74 @@ render_bwd_kernel(const uint2* __restrict__ ranges, const char* __restrict__ bin
 #pragma unroll
       for (int blk = 0; blk < BWD_WARPS; blk++) {
         const unsigned word = __ballot_sync(0xffffffffu, (m >> blk) & 1u);
-        if (lane == 0) s_bits[stage][blk][wid] = word;
+        if (lane == 0) S.bits[stage][blk] = word;
       }
     }
+  };
+
+  // phase 2: lane (k = lane & 15, half = lane >> 4) sums record k of the chunk over pixels half*16 .. +15
+  const int ck = lane & (CH - 1), chalf = lane >> 4;
+  auto phase2 = [&](int n, int stage, uint32_t& mymask) {
+    __syncwarp();
+    const bool have = ck < n;
+    const uint32_t e = have ? S.chunk_e[wid][ck] : 0u;
+    const float4 ra = S.rec[stage][e][0];   // mx, my, con.x, con.y
+    const float4 rb = S.rec[stage][e][1];   // con.z, opac, depth
+    float s0 = 0, s1 = 0, s2 = 0, s3 = 0, s4 = 0, s5 = 0, s6 = 0;      // sum w * dL/dpix_c
+    float sh = 0, shx = 0, shy = 0, shxx = 0, shxy = 0, shyy = 0, sab = 0;
+    const int pbase = wid * 32 + chalf * 16;
+#pragma unroll 4
+    for (int i = 0; i < 16; i++) {
+      const float2 wh = S.wh[wid][chalf * 16 + i][ck];
+      const float4 p0 = *reinterpret_cast<const float4*>(&S.pix[pbase + i][0]);
+      const float4 p1 = *reinterpret_cast<const float4*>(&S.pix[pbase + i][4]);
+      const float pyv = S.pix[pbase + i][8];
+      s0 = fmaf(wh.x, p0.x, s0); s1 = fmaf(wh.x, p0.y, s1); s2 = fmaf(wh.x, p0.z, s2); s3 = fmaf(wh.x, p0.w, s3);
+      s4 = fmaf(wh.x, p1.x, s4); s5 = fmaf(wh.x, p1.y, s5); s6 = fmaf(wh.x, p1.z, s6);
+      const float dx = ra.x - p1.w, dy = ra.y - pyv;
+      const float hx = wh.y * dx, hy = wh.y * dy;
+      sh += wh.y; shx += hx; shy += hy;
+      shxx = fmaf(hx, dx, shxx); shxy = fmaf(hx, dy, shxy); shyy = fmaf(hy, dy, shyy);
+      const float t7 = fmaf(ra.z, hx, ra.w * hy), t8 = fmaf(rb.x, hy, ra.w * hx);
+      sab = fmaf(fabsf(t7), ddelx_dx, sab); sab = fmaf(fabsf(t8), ddely_dy, sab);
+    }
+#define XH(v) v += __shfl_xor_sync(0xffffffffu, v, 16)
+    XH(s0); XH(s1); XH(s2); XH(s3); XH(s4); XH(s5); XH(s6);
+    XH(sh); XH(shx); XH(shy); XH(shxx); XH(shxy); XH(shyy); XH(sab);
+#undef XH
+    if (have && chalf == 0) {
+      const float o = rb.y;
+      float4* out = reinterpret_cast<float4*>(&S.part[wid][e][0]);
+      out[0] = make_float4(s0, s1, s2, s3);
+      out[1] = make_float4(s4, s5, s6, -ddelx_dx * o * fmaf(ra.z, shx, ra.w * shy));
+      out[2] = make_float4(-ddely_dy * o * fmaf(rb.x, shy, ra.w * shx), fabsf(o) * sab, -0.5f * o * shxx, -0.5f * o * shxy);
+      out[3] = make_float4(-0.5f * o * shyy, sh, 0.f, 0.f);
+    }
+    mymask |= __reduce_or_sync(0xffffffffu, have ? (1u << e) : 0u);   // every lane owns a different record
+    __syncwarp();
   };
 
   issue(0, 0);
   for (int b = 0; b < nbatches; b++) {
     const int stage = b & 1;
     cp_async_wait_all();
-    __syncthreads();   // stage visible; previous flush finished reading s_part / s_mask
+    __syncthreads();   // stage visible; previous flush finished reading part / pmask
     if (b + 1 < nbatches) issue(b + 1, stage ^ 1);
     const int first_pos = used - 1 - b * BWD_BATCH;
     const int cnt = min(BWD_BATCH, first_pos + 1);
-    unsigned long long mymask = 0ull;
+    uint32_t mymask = 0u;
 
-    // entries this warp can use: reach bit set and pos < wmax  <=>  e >= first_pos - wmax + 1
+    // records this warp can use: reach bit set and pos < wmax  <=>  e >= first_pos - wmax + 1
     int e0 = first_pos - (int)wmax + 1;
     if (e0 < 0) e0 = 0;
-    for (int word = e0 >> 5; word < BWD_BATCH / 32; word++) {
-     unsigned bits = s_bits[stage][wid][word];
-     if (word == (e0 >> 5)) bits &= 0xffffffffu << (e0 & 31);
-     while (bits) {
-      const int e = word * 32 + __ffs(bits) - 1;
+    unsigned bits = e0 < 32 ? (S.bits[stage][wid] & (0xffffffffu << e0)) : 0u;
+    int kcur = 0;
+    while (bits) {
+      const int e = __ffs(bits) - 1;
       bits &= bits - 1;
       const int pos = first_pos - e;
-      const float4 ra = s_rec[stage][e][0];   // mx, my, con.x, con.y
-      const float4 rb = s_rec[stage][e][1];   // con.z, opac, depth
+      const float4 ra = S.rec[stage][e][0];   // mx, my, con.x, con.y
+      const float4 rb = S.rec[stage][e][1];   // con.z, opac, depth
       const float dx = ra.x - pixfx, dy = ra.y - pixfy;
       const float power = -0.5f * (ra.z * dx * dx + rb.x * dy * dy) - ra.w * dx * dy;
       const float G = exp(power);
@@ -206,12 +231,10 @@ render_bwd_kernel(const uint2* __restrict__ ranges, const char* __restrict__ bin
       const bool active = ((uint32_t)pos < last_contributor) && !(power > 0.0f) && !(alpha < 1.0f / 255.0f);
       if (!__any_sync(0xffffffffu, active)) continue;
 
-      float v[16];
-#pragma unroll
-      for (int i = 0; i < 16; i++) v[i] = 0.f;
+      float w_out = 0.f, h_out = 0.f;
       if (active) {
-        const float4 rc = s_rec[stage][e][2];   // r, g, b, nx
-        const float4 rd = s_rec[stage][e][3];   // ny, nz
+        const float4 rc = S.rec[stage][e][2];   // r, g, b, nx
+        const float4 rd = S.rec[stage][e][3];   // ny, nz
         const float inv_1ma = __frcp_rn(1.f - alpha);   // shared by the T recovery and the background term
         T = T * inv_1ma;
         const float weight = alpha * T;
@@ -222,7 +245,7 @@ render_bwd_kernel(const uint2* __restrict__ ranges, const char* __restrict__ bin
         g_last = g;
         float dL_dalpha = g - A;
         if (HAS_EXTRA) {
-          const uint32_t gid = s_id[stage][e];
+          const uint32_t gid = S.id[stage][e];
           for (int ch = 0; ch < ED; ch++) {
             const float ex = extras[(size_t)gid * ED + ch];
             accum_ree[ch] = last_alpha * last_extra[ch] + (1.f - last_alpha) * accum_ree[ch];
@@ -234,30 +257,17 @@ render_bwd_kernel(const uint2* __restrict__ ranges, const char* __restrict__ bin
         dL_dalpha *= T;
         last_alpha = alpha;
         dL_dalpha += (-T_final * inv_1ma) * bg_dot;
-
-        const float dL_dG = rb.y * dL_dalpha;
-        const float gdx = G * dx, gdy = G * dy;
-        const float dG_ddelx = -gdx * ra.z - gdy * ra.w;
-        const float dG_ddely = -gdy * rb.x - gdx * ra.w;
-        v[0] = weight * dLc0; v[1] = weight * dLc1; v[2] = weight * dLc2;
-        v[3] = weight * dLd;
-        v[4] = weight * dLn0; v[5] = weight * dLn1; v[6] = weight * dLn2;
-        v[7] = dL_dG * dG_ddelx * ddelx_dx;
-        v[8] = dL_dG * dG_ddely * ddely_dy;
-        v[9] = fabsf(v[7]) + fabsf(v[8]);
-        v[10] = -0.5f * gdx * dx * dL_dG;
-        v[11] = -0.5f * gdx * dy * dL_dG;
-        v[12] = -0.5f * gdy * dy * dL_dG;
-        v[13] = G * dL_dalpha;
+        w_out = weight;
+        h_out = G * dL_dalpha;
       }
-      const float z = butterfly16(v, lane);
-      if ((lane & 1) == 0) s_part[wid][e][lane >> 1] = z;
-      mymask |= (1ull << e);
-     }
+      S.wh[wid][lane][kcur] = make_float2(w_out, h_out);
+      if (lane == 0) S.chunk_e[wid][kcur] = (uint32_t)e;
+      if (++kcur == CH) { phase2(CH, stage, mymask); kcur = 0; }
     }
-    if (lane == 0) s_mask[wid] = mymask;
+    if (kcur) phase2(kcur, stage, mymask);
+    if (lane == 0) S.pmask[wid] = mymask;
     __syncthreads();
-    // flush: thread -> (entry, quarter); fixed warp order => deterministic per tile
+    // flush: thread -> (record, quarter); fixed warp order => deterministic per tile
     {
       const int e = tid >> 2, q = tid & 3;
       if (e < cnt) {
@@ -265,13 +275,13 @@ render_bwd_kernel(const uint2* __restrict__ ranges, const char* __restrict__ bin
         bool any = false;
 #pragma unroll
         for (int w = 0; w < BWD_WARPS; w++) {
-          if ((s_mask[w] >> e) & 1ull) {
-            const float4 p = *reinterpret_cast<const float4*>(&s_part[w][e][q * 4]);
+          if ((S.pmask[w] >> e) & 1u) {
+            const float4 p = *reinterpret_cast<const float4*>(&S.part[w][e][q * 4]);
             s.x += p.x; s.y += p.y; s.z += p.z; s.w += p.w;
             any = true;
           }
         }
-        if (any) red_add_v4(acc + (size_t)s_id[stage][e] * 16 + q * 4, s);
+        if (any) red_add_v4(acc + (size_t)S.id[stage][e] * 16 + q * 4, s);
       }
     }
   }
@@ -285,16 +295,22 @@ void sfgs_launch_render_bwd(const sfgs_backward_args* a, const GeomLayout& g, co
   const int band1 = a->tile_row_end > a->tile_row_begin ? (a->tile_row_end < im.tiles_y ? a->tile_row_end : im.tiles_y) : im.tiles_y;
   if (band1 <= band0) return;
   dim3 grid(im.tiles_x, band1 - band0, 1);
+  const size_t smem = sizeof(BwdSmem);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(render_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(render_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr_set = true;
+  }
   SFGS_COUNT_LAUNCH();
   if (a->ED > 0)
-    render_bwd_kernel<true><<<grid, BWD_THREADS, 0, st>>>(
-        im.ranges, (const char*)b.point_list, im.hdr, a->width, a->height, a->ED, band0, a->background, g.rec, a->extra_attrs,
-        a->accum_alphas,
-        im.n_contrib, a->dL_dpix, a->dL_dpix_depth, a->dL_dpix_norm, a->dL_dpix_alpha, a->dL_dpix_extra, acc,
-        a->dL_dextra);
+    render_bwd_kernel<true><<<grid, BWD_THREADS, smem, st>>>(
+        im.ranges, (const char*)b.point_list, im.hdr, a->width, a->height, a->ED, band0, a->background, g.rec,
+        a->extra_attrs, a->accum_alphas, im.n_contrib, a->dL_dpix, a->dL_dpix_depth, a->dL_dpix_norm,
+        a->dL_dpix_alpha, a->dL_dpix_extra, acc, a->dL_dextra);
   else
-    render_bwd_kernel<false><<<grid, BWD_THREADS, 0, st>>>(
+    render_bwd_kernel<false><<<grid, BWD_THREADS, smem, st>>>(
         im.ranges, (const char*)b.point_list, im.hdr, a->width, a->height, 0, band0, a->background, g.rec, nullptr,
-        a->accum_alphas,
-        im.n_contrib, a->dL_dpix, a->dL_dpix_depth, a->dL_dpix_norm, a->dL_dpix_alpha, nullptr, acc, nullptr);
+        a->accum_alphas, im.n_contrib, a->dL_dpix, a->dL_dpix_depth, a->dL_dpix_norm, a->dL_dpix_alpha, nullptr, acc,
+        nullptr);
 }

@@ -30,6 +30,8 @@ def _ptr(t, keep):
     if not t.is_cuda:
         raise ValueError("tensor must live on a CUDA device")
     tc = t.contiguous()
+    if tc.data_ptr() % 16:          # offset views: the kernels use 128-bit loads on [P,4] / [P,16,3] rows
+        tc = tc.clone()
     keep.append(tc)
     return tc.data_ptr()
 
@@ -135,11 +137,12 @@ def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rot
     with torch.cuda.device(dev):
         # one allocation for all fixed-width per-Gaussian gradients (every element is written by the kernel)
         widths = dict(means3D=3, means2D=3, colors=3, depths=1, conic=4, opacity=1, cov3D=6, norm3D=3, scales=3, rot=4)
-        flat = torch.empty((P * sum(widths.values()),), **fopt)
+        pad = lambda n: (n + 3) & ~3                       # keep every sub-array 16-byte aligned  # noqa: E731
+        flat = torch.empty((sum(pad(P * w) for w in widths.values()),), **fopt)
         outs, off = {}, 0
         for k, w in widths.items():
             outs[k] = flat[off:off + P * w].view(P, w)
-            off += P * w
+            off += pad(P * w)
         dL_dsh = torch.empty((P, M, 3), **fopt) if M > 0 else torch.zeros((P, 0, 3), **fopt)
         dL_dextra = torch.empty((P, F), **fopt) if F > 0 else torch.empty(0, **fopt)
         scratch = _Arena(dev)
