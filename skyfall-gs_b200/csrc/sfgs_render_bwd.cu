@@ -18,29 +18,29 @@
 //     so each lane streams down its record's column of the tile accumulating in registers — no cross-lane
 //     reduction except one 16-lane exchange between the two pixel halves.  This replaces the 16-shuffle
 //     butterfly per (warp, record) of the first version of this kernel (~45 % fewer issued instructions).
-//   combine: the 8 warps' partial sums meet in shared-memory slots in a fixed order and one
-//     red.global.add.v4.f32 per (tile, Gaussian, quarter) reaches HBM: ~1000x fewer global atomics than the
-//     reference, deterministic inside a tile.
+//     A chunk is filled across staging batches (the record's parameters travel with it), so phase 2 always
+//     runs on 16 records except once at the end of the tile.
+//   combine: each (block, record) pair ends in four red.global.add.v4.f32 (measured: the L2 sustains
+//     ~320 G vector reductions/s, tools/red_bench.cu, so the ~16 M issued per frame hide behind the math):
+//     ~200x fewer global atomics than the reference and no block-wide barrier besides the staging one.
 #include "sfgs_common.cuh"
 
 namespace {
 
 constexpr int BWD_THREADS = 256;
 constexpr int BWD_WARPS = BWD_THREADS / 32;
-constexpr int BWD_BATCH = 32;     // records staged per step
+constexpr int BWD_BATCH = 64;     // records staged per step
 constexpr int CH = 16;            // records per phase-2 chunk
 constexpr int PIXF = 12;          // floats per pixel-table row: dLc[3], dLd, dLn[3], px, py, pad[3]
 
 struct BwdSmem {
-  float4 rec[2][BWD_BATCH][4];                 // 4 KB   staged blend records
+  float4 rec[2][BWD_BATCH][4];                 // 8 KB   staged blend records
   uint32_t id[2][BWD_BATCH];
-  uint32_t bits[2][BWD_WARPS];                 // per block: which staged records can reach it
-  float part[BWD_WARPS][BWD_BATCH][16];        // 16 KB  per-warp partial sums of the current batch
-  uint32_t pmask[BWD_WARPS];                   // which records of the batch each warp wrote
+  uint32_t bits[2][BWD_WARPS][BWD_BATCH / 32]; // per block: which staged records can reach it
   uint32_t maxc[BWD_WARPS];
   float2 wh[BWD_WARPS][32][CH + 1];            // 34 KB  phase-1 -> phase-2 hand-over, [pixel][record], padded
   float pix[BWD_THREADS][PIXF];                // 12 KB  per-pixel cotangents and coordinates
-  uint32_t chunk_e[BWD_WARPS][CH];             // record index (within the batch) of every chunk slot
+  float4 cparam[BWD_WARPS][CH][2];             // 4 KB   per chunk slot: (mx,my,con.x,con.y), (con.z,opac,id bits,-)
 };
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
@@ -156,19 +156,18 @@ render_bwd_kernel(const uint2* __restrict__ ranges, const char* __restrict__ bin
 #pragma unroll
       for (int blk = 0; blk < BWD_WARPS; blk++) {
         const unsigned word = __ballot_sync(0xffffffffu, (m >> blk) & 1u);
-        if (lane == 0) S.bits[stage][blk] = word;
+        if (lane == 0) S.bits[stage][blk][wid] = word;
       }
     }
   };
 
   // phase 2: lane (k = lane & 15, half = lane >> 4) sums record k of the chunk over pixels half*16 .. +15
   const int ck = lane & (CH - 1), chalf = lane >> 4;
-  auto phase2 = [&](int n, int stage, uint32_t& mymask) {
+  auto phase2 = [&](int n) {
     __syncwarp();
     const bool have = ck < n;
-    const uint32_t e = have ? S.chunk_e[wid][ck] : 0u;
-    const float4 ra = S.rec[stage][e][0];   // mx, my, con.x, con.y
-    const float4 rb = S.rec[stage][e][1];   // con.z, opac, depth
+    const float4 ra = S.cparam[wid][ck][0];   // mx, my, con.x, con.y
+    const float4 rb = S.cparam[wid][ck][1];   // con.z, opac, id bits
     float s0 = 0, s1 = 0, s2 = 0, s3 = 0, s4 = 0, s5 = 0, s6 = 0;      // sum w * dL/dpix_c
     float sh = 0, shx = 0, shy = 0, shxx = 0, shxy = 0, shyy = 0, sab = 0;
     const int pbase = wid * 32 + chalf * 16;
@@ -191,100 +190,86 @@ render_bwd_kernel(const uint2* __restrict__ ranges, const char* __restrict__ bin
     XH(s0); XH(s1); XH(s2); XH(s3); XH(s4); XH(s5); XH(s6);
     XH(sh); XH(shx); XH(shy); XH(shxx); XH(shxy); XH(shyy); XH(sab);
 #undef XH
-    if (have && chalf == 0) {
+    if (have) {
       const float o = rb.y;
-      float4* out = reinterpret_cast<float4*>(&S.part[wid][e][0]);
-      out[0] = make_float4(s0, s1, s2, s3);
-      out[1] = make_float4(s4, s5, s6, -ddelx_dx * o * fmaf(ra.z, shx, ra.w * shy));
-      out[2] = make_float4(-ddely_dy * o * fmaf(rb.x, shy, ra.w * shx), fabsf(o) * sab, -0.5f * o * shxx, -0.5f * o * shxy);
-      out[3] = make_float4(-0.5f * o * shyy, sh, 0.f, 0.f);
+      float* dst = acc + (size_t)__float_as_uint(rb.z) * 16;
+      if (chalf == 0) {
+        red_add_v4(dst, make_float4(s0, s1, s2, s3));
+        red_add_v4(dst + 4, make_float4(s4, s5, s6, -ddelx_dx * o * fmaf(ra.z, shx, ra.w * shy)));
+      } else {
+        red_add_v4(dst + 8, make_float4(-ddely_dy * o * fmaf(rb.x, shy, ra.w * shx), fabsf(o) * sab, -0.5f * o * shxx,
+                                        -0.5f * o * shxy));
+        red_add_v4(dst + 12, make_float4(-0.5f * o * shyy, sh, 0.f, 0.f));
+      }
     }
-    mymask |= __reduce_or_sync(0xffffffffu, have ? (1u << e) : 0u);   // every lane owns a different record
     __syncwarp();
   };
 
   issue(0, 0);
+  int kcur = 0;   // fill level of this warp's chunk; persists across batches
   for (int b = 0; b < nbatches; b++) {
     const int stage = b & 1;
     cp_async_wait_all();
-    __syncthreads();   // stage visible; previous flush finished reading part / pmask
+    __syncthreads();   // stage visible to all; the other stage is no longer read by anyone
     if (b + 1 < nbatches) issue(b + 1, stage ^ 1);
     const int first_pos = used - 1 - b * BWD_BATCH;
-    const int cnt = min(BWD_BATCH, first_pos + 1);
-    uint32_t mymask = 0u;
 
     // records this warp can use: reach bit set and pos < wmax  <=>  e >= first_pos - wmax + 1
     int e0 = first_pos - (int)wmax + 1;
     if (e0 < 0) e0 = 0;
-    unsigned bits = e0 < 32 ? (S.bits[stage][wid] & (0xffffffffu << e0)) : 0u;
-    int kcur = 0;
-    while (bits) {
-      const int e = __ffs(bits) - 1;
-      bits &= bits - 1;
-      const int pos = first_pos - e;
-      const float4 ra = S.rec[stage][e][0];   // mx, my, con.x, con.y
-      const float4 rb = S.rec[stage][e][1];   // con.z, opac, depth
-      const float dx = ra.x - pixfx, dy = ra.y - pixfy;
-      const float power = -0.5f * (ra.z * dx * dx + rb.x * dy * dy) - ra.w * dx * dy;
-      const float G = exp(power);
-      const float alpha = min(0.99f, rb.y * G);
-      const bool active = ((uint32_t)pos < last_contributor) && !(power > 0.0f) && !(alpha < 1.0f / 255.0f);
-      if (!__any_sync(0xffffffffu, active)) continue;
+    for (int word = e0 >> 5; word < BWD_BATCH / 32; word++) {
+      unsigned bits = S.bits[stage][wid][word];
+      if (word == (e0 >> 5)) bits &= 0xffffffffu << (e0 & 31);
+      while (bits) {
+        const int e = word * 32 + __ffs(bits) - 1;
+        bits &= bits - 1;
+        const int pos = first_pos - e;
+        const float4 ra = S.rec[stage][e][0];   // mx, my, con.x, con.y
+        const float4 rb = S.rec[stage][e][1];   // con.z, opac, depth
+        const float dx = ra.x - pixfx, dy = ra.y - pixfy;
+        const float power = -0.5f * (ra.z * dx * dx + rb.x * dy * dy) - ra.w * dx * dy;
+        const float G = exp(power);
+        const float alpha = min(0.99f, rb.y * G);
+        const bool active = ((uint32_t)pos < last_contributor) && !(power > 0.0f) && !(alpha < 1.0f / 255.0f);
+        if (!__any_sync(0xffffffffu, active)) continue;
 
-      float w_out = 0.f, h_out = 0.f;
-      if (active) {
-        const float4 rc = S.rec[stage][e][2];   // r, g, b, nx
-        const float4 rd = S.rec[stage][e][3];   // ny, nz
-        const float inv_1ma = __frcp_rn(1.f - alpha);   // shared by the T recovery and the background term
-        T = T * inv_1ma;
-        const float weight = alpha * T;
-        float g = rc.x * dLc0;
-        g += rc.y * dLc1; g += rc.z * dLc2; g += rb.z * dLd;
-        g += rc.w * dLn0; g += rd.x * dLn1; g += rd.y * dLn2; g += dLa;
-        A = last_alpha * g_last + (1.f - last_alpha) * A;
-        g_last = g;
-        float dL_dalpha = g - A;
-        if (HAS_EXTRA) {
-          const uint32_t gid = S.id[stage][e];
-          for (int ch = 0; ch < ED; ch++) {
-            const float ex = extras[(size_t)gid * ED + ch];
-            accum_ree[ch] = last_alpha * last_extra[ch] + (1.f - last_alpha) * accum_ree[ch];
-            last_extra[ch] = ex;
-            dL_dalpha += (ex - accum_ree[ch]) * dL_dpixel_extra[ch];
-            atomicAdd(&dL_dextras[(size_t)gid * ED + ch], weight * dL_dpixel_extra[ch]);
+        float w_out = 0.f, h_out = 0.f;
+        if (active) {
+          const float4 rc = S.rec[stage][e][2];   // r, g, b, nx
+          const float4 rd = S.rec[stage][e][3];   // ny, nz
+          const float inv_1ma = __frcp_rn(1.f - alpha);   // shared by the T recovery and the background term
+          T = T * inv_1ma;
+          const float weight = alpha * T;
+          float g = rc.x * dLc0;
+          g += rc.y * dLc1; g += rc.z * dLc2; g += rb.z * dLd;
+          g += rc.w * dLn0; g += rd.x * dLn1; g += rd.y * dLn2; g += dLa;
+          A = last_alpha * g_last + (1.f - last_alpha) * A;
+          g_last = g;
+          float dL_dalpha = g - A;
+          if (HAS_EXTRA) {
+            const uint32_t gid = S.id[stage][e];
+            for (int ch = 0; ch < ED; ch++) {
+              const float ex = extras[(size_t)gid * ED + ch];
+              accum_ree[ch] = last_alpha * last_extra[ch] + (1.f - last_alpha) * accum_ree[ch];
+              last_extra[ch] = ex;
+              dL_dalpha += (ex - accum_ree[ch]) * dL_dpixel_extra[ch];
+              atomicAdd(&dL_dextras[(size_t)gid * ED + ch], weight * dL_dpixel_extra[ch]);
+            }
           }
+          dL_dalpha *= T;
+          last_alpha = alpha;
+          dL_dalpha += (-T_final * inv_1ma) * bg_dot;
+          w_out = weight;
+          h_out = G * dL_dalpha;
         }
-        dL_dalpha *= T;
-        last_alpha = alpha;
-        dL_dalpha += (-T_final * inv_1ma) * bg_dot;
-        w_out = weight;
-        h_out = G * dL_dalpha;
-      }
-      S.wh[wid][lane][kcur] = make_float2(w_out, h_out);
-      if (lane == 0) S.chunk_e[wid][kcur] = (uint32_t)e;
-      if (++kcur == CH) { phase2(CH, stage, mymask); kcur = 0; }
-    }
-    if (kcur) phase2(kcur, stage, mymask);
-    if (lane == 0) S.pmask[wid] = mymask;
-    __syncthreads();
-    // flush: thread -> (record, quarter); fixed warp order => deterministic per tile
-    {
-      const int e = tid >> 2, q = tid & 3;
-      if (e < cnt) {
-        float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-        bool any = false;
-#pragma unroll
-        for (int w = 0; w < BWD_WARPS; w++) {
-          if ((S.pmask[w] >> e) & 1u) {
-            const float4 p = *reinterpret_cast<const float4*>(&S.part[w][e][q * 4]);
-            s.x += p.x; s.y += p.y; s.z += p.z; s.w += p.w;
-            any = true;
-          }
-        }
-        if (any) red_add_v4(acc + (size_t)S.id[stage][e] * 16 + q * 4, s);
+        S.wh[wid][lane][kcur] = make_float2(w_out, h_out);
+        if (lane == 0) S.cparam[wid][kcur][0] = ra;
+        if (lane == 1) S.cparam[wid][kcur][1] = make_float4(rb.x, rb.y, __uint_as_float(S.id[stage][e]), 0.f);
+        if (++kcur == CH) { phase2(CH); kcur = 0; }
       }
     }
   }
+  if (kcur) phase2(kcur);
 }
 
 }  // namespace
