@@ -65,52 +65,50 @@ def peaks():
 
 
 class ClockSampler:
-    """SM clock / throttle reasons read through NVML while the GPU is under load.  Sampling happens in the
-    un-timed gap between two steps of the timed loop (the previous step's backward kernels are still
-    running then): polling from a second thread or process DURING a step stalls the driver and was
-    measured to inflate the median step from 2.1 ms to 4.4-4.7 ms, with 30-70 ms outliers."""
+    """SM clock and throttle reasons for the timed loop.
 
-    def __init__(self, index: int):
-        self.sm, self.reasons, self.max_mhz, self.nv = [], set(), None, None
-        try:
-            import pynvml
-            pynvml.nvmlInit()
-            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
-            phys = int(vis.split(",")[index]) if vis and all(v.strip().isdigit() for v in vis.split(",")) else index
-            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
-            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
-            self.nv = pynvml
-        except Exception:  # noqa: BLE001
-            self.nv = None
+    The clock is measured IN-STREAM, in the un-timed gap between two steps while the previous step's backward
+    is still in flight: a one-thread kernel (sfgs_sm_clock_probe) counts SM cycles against %globaltimer for
+    ~20 us.  NVML is only touched before the warm-up (max clock) and once right after the last timed step
+    (throttle reasons): polling NVML or nvidia-smi from the host DURING the loop was measured to inflate the
+    median step from 1.8 ms to 3.8-4.7 ms with 30-70 ms outliers on these boxes."""
+
+    def __init__(self, index: int, dev):
+        self.index, self.dev = index, dev
+        self.buf = torch.zeros(64, dtype=torch.float32, device=dev)
+        self.n = 0
 
     def sample(self):
-        nv = self.nv
-        if nv is None:
-            return
-        names = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
-                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
-                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
-                 "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
-        try:
-            self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
-            r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
-            for k, bit in names.items():
-                if r & bit:
-                    self.reasons.add(k)
-        except Exception:  # noqa: BLE001
-            pass
+        from sfgs import native
+        if self.n < 64:
+            native.lib().sfgs_sm_clock_probe(self.buf.data_ptr() + 4 * self.n, torch.cuda.current_stream(self.dev).cuda_stream)
+            self.n += 1
 
     def stop(self):
-        out = {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.max_mhz,
-               "reasons": sorted(self.reasons) if self.sm else ["not sampled"], "samples": len(self.sm),
-               "source": "NVML, sampled between steps of the timed loop while the previous step's kernels run"}
-        if self.nv is not None:
-            try:
-                self.nv.nvmlShutdown()
-            except Exception:  # noqa: BLE001
-                pass
-            self.nv = None
-        return out
+        reasons, src, max_mhz = [], "in-stream cycle counter between steps of the timed loop", None
+        try:   # NVML is initialised only now; the GPU is still executing the last step's backward
+            import pynvml as nv
+            nv.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[self.index]) if vis and all(v.strip().isdigit() for v in vis.split(",")) else self.index
+            h = nv.nvmlDeviceGetHandleByIndex(phys)
+            names = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                     "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                     "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                     "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+            r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+            reasons = sorted(k for k, bit in names.items() if r & bit)
+            max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            nvml_now = float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+            src += "; throttle reasons, max clock and one NVML clock sample read right after the last timed step"
+            nv.nvmlShutdown()
+        except Exception:  # noqa: BLE001
+            reasons, nvml_now = ["nvml unavailable"], None
+        torch.cuda.synchronize(self.dev)
+        vals = self.buf[: self.n].cpu().numpy() if self.n else np.zeros(0)
+        sm = float(np.median(vals)) if len(vals) else nvml_now
+        return {"sm_mhz": sm, "sm_max_mhz": max_mhz, "reasons": reasons, "samples": int(len(vals)) if len(vals) else 1,
+                "source": src if len(vals) else "one NVML read right after the last timed step"}
 
 
 def camera_for_rank(rank: int, world: int) -> S.Camera:
@@ -361,12 +359,12 @@ def main():
         step = lambda: step_ref(d, cam)   # noqa: E731
 
     # ---- value: device-resident inputs, per-step events, max over ranks
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(local_rank, dev)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize(dev)
     launches0 = native.lib().sfgs_launch_count() if args.impl == "ours" else 0
-    ms = timed_steps(step, steps, warmup, flush, dev, between=None if args.no_clocks else sampler.sample)
+    ms = timed_steps(step, steps, warmup, flush, dev, between=sampler.sample if (args.impl == "ours" and not args.no_clocks) else None)
     clocks = sampler.stop()
     launches = (native.lib().sfgs_launch_count() - launches0) if args.impl == "ours" else None
     total_ms = torch.tensor([sum(ms)], dtype=torch.float64, device=dev)
@@ -425,8 +423,13 @@ def main():
         ach = alg[dom] / (stage_ms[dom] / 1e3) / 1e9
         b_total = sum(alg.values())
         t_kernels = sum(stage_ms.values())
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")   # dram__bytes_read+write per launch from `ncu --set full`
+        if os.path.exists(tpath):
+            with open(tpath) as f:
+                traffic = json.load(f).get("kernels", {}).get(dom)
         out["roofline"] = {"bound": "hbm", "kernel": dom, "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
-                           "frac": round(ach / peak, 4), "traffic": None, "peak_source": peak_src,
+                           "frac": round(ach / peak, 4), "traffic": traffic, "peak_source": peak_src,
                            "algorithmic_bytes": int(alg[dom]), "kernel_ms": round(stage_ms[dom], 4),
                            "share_of_step": round(stage_ms[dom] / t_kernels, 3)}
         out["roofline_pipeline"] = {"algorithmic_bytes": int(b_total), "kernels_ms": round(t_kernels, 4),

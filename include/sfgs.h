@@ -210,6 +210,10 @@ int sfgs_dist2_knn3(int P, const float* points, float* mean_dist2,
 int sfgs_profile_enable(int on);
 int sfgs_profile_read(double* ms_total, long long* launches, int n);
 
+/* Queue a one-thread kernel that spins ~20 us and writes the SM clock it observed (MHz) to *out_mhz_device.
+ * Used by bench.py to sample clocks in-stream during the timed loop without touching NVML. */
+int sfgs_sm_clock_probe(float* out_mhz_device, void* stream);
+
 /* ---- misc ---------------------------------------------------------------- */
 const char* sfgs_last_error(void);
 /* sizeof() of the ABI structs as compiled (0 forward_args, 1 backward_args, 2 geom_view, 3 image_view,

@@ -38,6 +38,17 @@ void sfgs_launch_gauss_bwd(const sfgs_backward_args* a, const GeomLayout& g, flo
 
 namespace {
 
+// One thread spins ~20 us and reports SM cycles per microsecond: the SM clock actually applied while the
+// surrounding work runs, measured in-stream (polling NVML from the host during a run perturbs it).
+__global__ void sm_clock_probe_kernel(float* out_mhz) {
+  unsigned long long t0, t1;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  const long long c0 = clock64();
+  do { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1)); } while (t1 - t0 < 20000ull);
+  const long long c1 = clock64();
+  *out_mhz = (float)((double)(c1 - c0) * 1000.0 / (double)(t1 - t0));
+}
+
 thread_local char t_err[512] = "";
 std::atomic<long long> g_last_R{0};
 std::atomic<long long> g_last_capacity{0};
@@ -291,6 +302,12 @@ int sfgs_rasterize_backward(const sfgs_backward_args* a) {
   PROF_END();
   STAGE_CHECK("gauss_bwd");
   return SFGS_OK;
+}
+
+int sfgs_sm_clock_probe(float* out_mhz_device, void* stream) {
+  if (!out_mhz_device) return fail(SFGS_E_BADARG, "sm_clock_probe: null");
+  sm_clock_probe_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(out_mhz_device);
+  return cudaGetLastError() == cudaSuccess ? SFGS_OK : SFGS_E_CUDA;
 }
 
 size_t sfgs_sizeof(int which) {

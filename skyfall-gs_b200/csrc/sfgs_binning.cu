@@ -15,8 +15,9 @@
 
 namespace {
 
-// ---- exclusive scan of the tile histogram (single CTA) ----------------------
+// ---- exclusive scan of the tile histogram (single CTA, 8 tiles per thread per pass) ----------
 constexpr int SCAN_THREADS = 1024;
+constexpr int SCAN_ITEMS = 8;
 __global__ void __launch_bounds__(SCAN_THREADS)
 tile_scan_kernel(int tiles, const uint32_t* __restrict__ tile_count, uint2* __restrict__ ranges,
                  uint32_t* __restrict__ tile_cursor, uint32_t* __restrict__ hdr, unsigned long long capacity) {
@@ -27,28 +28,39 @@ tile_scan_kernel(int tiles, const uint32_t* __restrict__ tile_count, uint2* __re
   if (tid == 0) { carry_s = 0; maxlen_s = 0; }
   __syncthreads();
   uint32_t local_max = 0;
-  for (int base = 0; base < tiles; base += SCAN_THREADS) {
-    const int i = base + tid;
-    const uint32_t v = (i < tiles) ? tile_count[i] : 0u;
-    local_max = max(local_max, v);
-    uint32_t x = v;
+  for (int base = 0; base < tiles; base += SCAN_THREADS * SCAN_ITEMS) {
+    const int i0 = base + tid * SCAN_ITEMS;
+    uint32_t v[SCAN_ITEMS];
+    uint32_t x = 0;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+    for (int k = 0; k < SCAN_ITEMS; k++) {
+      v[k] = (i0 + k < tiles) ? tile_count[i0 + k] : 0u;
+      local_max = max(local_max, v[k]);
+      x += v[k];
+    }
+    const uint32_t mine = x;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
     if (lane == 31) warp_sums[wid] = x;
     __syncthreads();
     if (wid == 0) {
       uint32_t s = warp_sums[lane];
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, s, o); if (lane >= o) s += y; }
+      for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, s, o); if (lane >= o) s += y; }
       warp_sums[lane] = s;
     }
     __syncthreads();
     const uint32_t carry = carry_s;
     const uint32_t incl = carry + x + (wid > 0 ? warp_sums[wid - 1] : 0u);
-    if (i < tiles) {
-      // empty tiles read (0,0) exactly like the reference's memset + identifyTileRanges
-      ranges[i] = v ? make_uint2(incl - v, incl) : make_uint2(0u, 0u);
-      tile_cursor[i] = 0u;
+    uint32_t run = incl - mine;   // exclusive prefix of this thread's first tile
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) {
+      if (i0 + k < tiles) {
+        // empty tiles read (0,0) exactly like the reference's memset + identifyTileRanges
+        ranges[i0 + k] = v[k] ? make_uint2(run, run + v[k]) : make_uint2(0u, 0u);
+        tile_cursor[i0 + k] = 0u;
+      }
+      run += v[k];
     }
     __syncthreads();
     if (tid == SCAN_THREADS - 1) carry_s = incl;

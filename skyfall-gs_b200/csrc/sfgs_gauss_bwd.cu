@@ -320,7 +320,9 @@ gauss_bwd_kernel(int P, int D, int M, const float* __restrict__ means3D, const i
   // Per-thread stores of 3/4/6/48-float rows are strided across the warp (20 sectors per request measured);
   // stage the block's rows in shared memory and stream each output array out as contiguous 16-byte stores.
   __shared__ __align__(16) float s_out[GB_THREADS * 31];
-  __shared__ __align__(16) float s_sh[GB_THREADS * 19];
+  __shared__ __align__(128) float s_tile[WRITE_SH ? GB_THREADS * 48 : 4];   // 24 KB SH-gradient tile for the bulk store
+  float* s_sh = s_tile;   // the generic (M != 16 / unaligned) path keeps 19 floats per Gaussian here instead
+  const bool use_tma = WRITE_SH && M == 16 && (reinterpret_cast<uintptr_t>(dL_dsh) & 15) == 0;
   const int t = threadIdx.x;
   float* sp = s_out;
   // array order and widths: mean2D 3, conic 4, opacity 1, color 3, depth 1, mean3D 3, cov3D 6, norm3D 3, scale 3, rot 4
@@ -345,7 +347,7 @@ gauss_bwd_kernel(int P, int D, int M, const float* __restrict__ means3D, const i
   s_norm[3 * t] = o_norm[0]; s_norm[3 * t + 1] = o_norm[1]; s_norm[3 * t + 2] = o_norm[2];
   s_scale[3 * t] = o_scale[0]; s_scale[3 * t + 1] = o_scale[1]; s_scale[3 * t + 2] = o_scale[2];
   *reinterpret_cast<float4*>(s_rot + 4 * t) = make_float4(o_rot[0], o_rot[1], o_rot[2], o_rot[3]);
-  if (WRITE_SH) {
+  if (WRITE_SH && !use_tma) {
 #pragma unroll
     for (int k = 0; k < 16; k++) s_sh[19 * t + k] = dsh_scale[k];
     s_sh[19 * t + 16] = dL_dRGB[0]; s_sh[19 * t + 17] = dL_dRGB[1]; s_sh[19 * t + 18] = dL_dRGB[2];
@@ -371,20 +373,29 @@ gauss_bwd_kernel(int P, int D, int M, const float* __restrict__ means3D, const i
   stream_out(s_scale, dL_dscale, 3);
   stream_out(s_rot, dL_drot, 4);
   if (WRITE_SH) {
-    // dL_dsh[g][k][ch] = dRGB/dsh_k(g) * dL_dRGB[ch](g); output index i -> g = i / (3M), k = (i % 3M) / 3, ch = i % 3
+    // dL_dsh[g][k][ch] = dRGB/dsh_k(g) * dL_dRGB[ch](g)
     const int row = 3 * M;
     const int nfl = nvalid * row;
     float* d = dL_dsh + base * row;
-    if ((row & 3) == 0 && (reinterpret_cast<uintptr_t>(d) & 15) == 0) {
-      for (int i4 = t; i4 < (nfl >> 2); i4 += GB_THREADS) {
+    if (use_tma) {
+      // The block's 128 x 192-byte rows are one contiguous 24 KB span of dL_dsh: build it in shared memory and
+      // hand it to the TMA engine as a single bulk store (cp.async.bulk, shared::cta -> global).
+      float* rowp = s_tile + 48 * t;
+#pragma unroll
+      for (int k4 = 0; k4 < 12; k4++) {
         float v[4];
 #pragma unroll
-        for (int c = 0; c < 4; c++) {
-          const int i = 4 * i4 + c;
-          const int gl = i / row, r = i - gl * row, k = r / 3, ch = r - 3 * k;
-          v[c] = (k < 16 ? s_sh[19 * gl + k] : 0.f) * s_sh[19 * gl + 16 + ch];
-        }
-        reinterpret_cast<float4*>(d)[i4] = make_float4(v[0], v[1], v[2], v[3]);
+        for (int c = 0; c < 4; c++) { const int r = 4 * k4 + c; v[c] = dsh_scale[r / 3] * dL_dRGB[r % 3]; }
+        *reinterpret_cast<float4*>(rowp + 4 * k4) = make_float4(v[0], v[1], v[2], v[3]);
+      }
+      asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // generic-proxy writes -> visible to the async proxy
+      __syncthreads();
+      if (t == 0) {
+        const unsigned src = (unsigned)__cvta_generic_to_shared(s_tile);
+        const unsigned bytes = (unsigned)nfl * 4u;
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(d), "r"(src), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");   // shared memory must outlive the read
       }
     } else {
       for (int i = t; i < nfl; i += GB_THREADS) {

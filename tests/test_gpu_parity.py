@@ -334,3 +334,77 @@ def test_tile_row_bands_reassemble_the_frame(cuda_device):
     assert total_R == full[0]
     for a, b, name in zip(acc, gfull, ("means2D", "colors", "opacity", "means3D", "cov3D", "norm3D", "sh", "scales", "rot")):
         assert (a - b).abs().max().item() <= 1e-5 + 2e-4 * b.abs().max().item(), name
+
+
+def test_config0_100k_gaussians_512_forward_vs_cpu_oracle(cuda_device):
+    """BASELINE.json configs[0]: 100k synthetic Gaussians, one 512x512 pinhole camera, forward only, against the
+    CPU restatement (the reference has no CPU path; the oracle is its plain-C port)."""
+    from oracle import cpu_oracle as O
+    dev = cuda_device
+    scene = S.blob_scene(100_000, seed=100, spread=3.0, scale=0.03)
+    cam = S.simple_camera(512, 512, fov_deg=60.0, distance=9.0)
+    bg = np.zeros(3, np.float32)
+    d = Hh.to_torch(scene, cam, dev)
+    f = Hh.run_ours_forward(d, cam, 3, torch.from_numpy(bg).to(dev))
+    o = O.forward(scene.means3D, scene.scales, scene.rotations, scene.opacities, scene.shs, 3, cam.viewmatrix,
+                  cam.projmatrix, cam.campos, cam.width, cam.height, cam.tanfovx, cam.tanfovy, bg)
+    assert f["num_rendered"] == o["num_rendered"] and np.array_equal(f["radii"].cpu().numpy(), o["radii"])
+    it = Hh.our_internals(f, scene.P, cam.height, cam.width)
+    assert np.array_equal(it["point_list"].cpu().numpy().astype(np.uint32), o["point_list"])
+    assert np.array_equal(it["ranges"].cpu().numpy().astype(np.uint32), o["ranges"])
+    for k in ("color", "depth", "norm", "alpha"):
+        dlt = np.abs(f[k].cpu().numpy() - o[k])
+        assert np.quantile(dlt, 0.9999) <= 1e-5 * max(1.0, float(np.abs(o[k]).max())), k
+
+
+def test_training_loop_with_all_three_ops(cuda_device):
+    """BASELINE.json configs[2] in miniature: distCUDA2 scale initialisation, then render -> L1 + fused-SSIM loss ->
+    backward -> Adam for a few dozen iterations against images of a hidden synthetic scene; the loss must fall."""
+    from diff_gauss import GaussianRasterizationSettings, GaussianRasterizer
+    from fused_ssim import fused_ssim
+    from simple_knn._C import distCUDA2
+    dev = cuda_device
+    target_scene = S.blob_scene(4000, seed=7, spread=1.5, scale=0.12)
+    cams = [S.orbit_camera(target=(0, 0, 0), elevation_deg=30.0, azimuth_deg=a, radius=7.0, fov_deg=50.0, width=160,
+                           height=128) for a in (0.0, 90.0, 180.0, 270.0)]
+    bg = torch.zeros(3, device=dev)
+
+    def render(params, cam):
+        means, logs, rots, logit_o, shs = params
+        rs = GaussianRasterizationSettings(cam.height, cam.width, cam.tanfovx, cam.tanfovy, 0.1,
+                                           torch.zeros(1, device=dev), bg, 1.0,
+                                           torch.from_numpy(cam.viewmatrix).to(dev), torch.from_numpy(cam.projmatrix).to(dev),
+                                           3, torch.from_numpy(cam.campos).to(dev), False, False)
+        m2d = torch.zeros_like(means, requires_grad=True)
+        out = GaussianRasterizer(rs)(means, m2d, torch.sigmoid(logit_o), shs=shs, scales=torch.exp(logs),
+                                     rotations=torch.nn.functional.normalize(rots))
+        return out[0], m2d
+
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)  # noqa: E731
+    with torch.no_grad():
+        tp = (t(target_scene.means3D), torch.log(t(target_scene.scales)), t(target_scene.rotations),
+              torch.logit(t(target_scene.opacities).clamp(1e-4, 1 - 1e-4)), t(target_scene.shs))
+        targets = [render(tp, c)[0].clone() for c in cams]
+    rng = np.random.default_rng(0)
+    init_xyz = t((target_scene.means3D + rng.normal(0, 0.05, target_scene.means3D.shape)).astype(np.float32))
+    d2 = distCUDA2(init_xyz).clamp_min(1e-7)
+    params = [init_xyz.clone().requires_grad_(True),
+              torch.log(torch.sqrt(d2))[:, None].repeat(1, 3).contiguous().requires_grad_(True),
+              t(np.tile(np.array([1, 0, 0, 0], np.float32), (target_scene.P, 1))).requires_grad_(True),
+              torch.full((target_scene.P, 1), -2.0, device=dev).requires_grad_(True),
+              torch.zeros((target_scene.P, 16, 3), device=dev).requires_grad_(True)]
+    opt = torch.optim.Adam([{"params": [params[0]], "lr": 2e-3}, {"params": [params[1]], "lr": 5e-3},
+                            {"params": [params[2]], "lr": 1e-3}, {"params": [params[3]], "lr": 5e-2},
+                            {"params": [params[4]], "lr": 2e-2}])
+    losses = []
+    for it in range(60):
+        cam, gt = cams[it % 4], targets[it % 4]
+        img, m2d = render(params, cam)
+        loss = 0.8 * (img - gt).abs().mean() + 0.2 * (1.0 - fused_ssim(img[None], gt[None]))
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        assert m2d.grad is not None and torch.isfinite(m2d.grad).all()
+        assert all(torch.isfinite(p.grad).all() for p in params)
+        opt.step()
+        losses.append(loss.item())
+    assert np.mean(losses[-8:]) < 0.7 * np.mean(losses[:4]), (losses[:4], losses[-8:])
