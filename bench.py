@@ -203,6 +203,28 @@ def timed_steps(step_fn, steps, warmup, flush, dev, between=None):
     return ms
 
 
+def measure(step_fn, steps, warmup, flush, dev, between=None, max_attempts=3):
+    """Time exactly `steps` steps; a pass disturbed by the host is rejected and re-measured (at most twice).
+
+    Every step launches ~10 kernels from Python and the forward waits once for the instance count, so a host
+    core that is descheduled for a few ms leaves the GPU idle inside the timed step.  On the shared boxes this
+    shows up as whole passes whose median step is 2-4x the pass minimum (observed on either leg, at random).
+    A pass counts as clean when its median is within 15 % of its fastest step; the reported pass is the first
+    clean one, or the pass with the smallest total if none is.  All attempts are listed in the JSON line."""
+    attempts = []
+    for k in range(max_attempts):
+        ms = timed_steps(step_fn, steps, warmup if k == 0 else 3, flush, dev, between)
+        srt = sorted(ms)
+        attempts.append(ms)
+        if srt[len(srt) // 2] <= 1.15 * srt[0]:
+            break
+    best = attempts[-1] if len(attempts) < max_attempts or sorted(attempts[-1])[len(ms) // 2] <= 1.15 * min(attempts[-1]) \
+        else min(attempts, key=sum)
+    info = {"attempts": len(attempts), "ms_per_step_of_each_attempt": [round(sum(a) / len(a), 4) for a in attempts],
+            "reported_min_ms": round(min(best), 4), "reported_median_ms": round(sorted(best)[len(best) // 2], 4)}
+    return best, info
+
+
 # ----------------------------------------------------------------------------- public-API leg ("e2e")
 class E2EOurs:
     """render -> L1-style loss -> backward through diff_gauss, with per-step H2D of camera + target image."""
@@ -363,10 +385,9 @@ def main():
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize(dev)
-    launches0 = native.lib().sfgs_launch_count() if args.impl == "ours" else 0
-    ms = timed_steps(step, steps, warmup, flush, dev, between=sampler.sample if (args.impl == "ours" and not args.no_clocks) else None)
+    ms, value_info = measure(step, steps, warmup, flush, dev,
+                             between=sampler.sample if (args.impl == "ours" and not args.no_clocks) else None)
     clocks = sampler.stop()
-    launches = (native.lib().sfgs_launch_count() - launches0) if args.impl == "ours" else None
     total_ms = torch.tensor([sum(ms)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.barrier()
@@ -376,7 +397,7 @@ def main():
 
     # ---- e2e: public API with host<->device copies inside the timed region
     e2e_obj = (E2EOurs if args.impl == "ours" else E2ERef)(scene, cam, dev)
-    e2e_ms = timed_steps(e2e_obj.step, steps, warmup, flush, dev)
+    e2e_ms, e2e_info = measure(e2e_obj.step, steps, warmup, flush, dev)
     e2e_total = torch.tensor([sum(e2e_ms)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(e2e_total, op=dist.ReduceOp.MAX)
@@ -400,12 +421,16 @@ def main():
            "e2e": {"value": round(e2e_value, 2), "unit": "Mpix/s", "h2d_bytes_per_step": (16 + 16 + 3) * 4 + 3 * N * 4,
                    "d2h_bytes_per_step": 4},
            "clocks": clocks}
+    out["timing"] = {"value": value_info, "e2e": e2e_info,
+                     "rule": "a pass whose median step exceeds 1.15x its fastest step is re-measured (<= 3 passes)"}
     out["e2e"]["api"] = ("diff_gauss.GaussianRasterizer + autograd" if args.impl == "ours"
                          else "reference CudaRasterizer::Rasterizer forward/backward")
     if args.impl == "ours":
-        out["gpu_launches"] = int(launches)
+        l0 = native.lib().sfgs_launch_count()
         f, _ = step()
         torch.cuda.synchronize(dev)
+        # kernels of this library launched inside the reported timed pass (steps x launches of one step)
+        out["gpu_launches"] = int(native.lib().sfgs_launch_count() - l0) * steps
         R, V = int(f[0]), int((f[5] > 0).sum().item())
         M = (SH_DEGREE + 1) ** 2
         tiles = ((cam.width + 15) // 16) * ((cam.height + 15) // 16)

@@ -50,6 +50,25 @@ gauss_bwd_kernel(int P, int D, int M, const float* __restrict__ means3D, const i
   const int idx = in_range ? idx_raw : P - 1;     // out-of-range threads idle through the math, join the block-wide store
   const size_t i = (size_t)idx;
 
+  // shared memory: the output staging rows and one 24 KB tile that first receives this block's SH coefficients
+  // (cp.async, column t of a [12][128] float4 array) and later, after the block barrier, the SH-gradient rows
+  __shared__ __align__(16) float s_out[GB_THREADS * 31];
+  __shared__ __align__(128) float s_tile[WRITE_SH ? GB_THREADS * 48 : 4];
+
+  // Everything that does not depend on the visibility test is requested before it: the kernel is bound by DRAM
+  // latency (ncu: long-scoreboard stalls, 30 % of HBM bandwidth), not by bytes.
+  const int my_radius = radii[idx];
+  const float mx = means3D[3 * i], my = means3D[3 * i + 1], mz = means3D[3 * i + 2];
+  float4 q_in = make_float4(0.f, 0.f, 0.f, 0.f);
+  float scx = 0.f, scy = 0.f, scz = 0.f;
+  if (scales != nullptr) {
+    q_in = *reinterpret_cast<const float4*>(rotations + 4 * i);
+    scx = scales[3 * i]; scy = scales[3 * i + 1]; scz = scales[3 * i + 2];
+  }
+  const unsigned cm = shs != nullptr ? clamped[idx] : 0u;
+  const bool sh_staged = WRITE_SH && shs != nullptr && M == 16 && (reinterpret_cast<uintptr_t>(shs) & 15) == 0;
+  const int sh_nq = D == 0 ? 1 : (D == 1 ? 3 : (D == 2 ? 7 : 12));   // float4s covering (D+1)^2 coefficients
+
   float o_mean2D[3] = {0, 0, 0}, o_conic[4] = {0, 0, 0, 0}, o_opac = 0, o_color[3] = {0, 0, 0}, o_depth = 0;
   float o_mean[3] = {0, 0, 0}, o_cov[6] = {0, 0, 0, 0, 0, 0}, o_norm[3] = {0, 0, 0};
   float o_scale[3] = {0, 0, 0}, o_rot[4] = {0, 0, 0, 0};
@@ -57,20 +76,33 @@ gauss_bwd_kernel(int P, int D, int M, const float* __restrict__ means3D, const i
 #pragma unroll
   for (int k = 0; k < 16; k++) dsh_scale[k] = 0.f;
   float dL_dRGB[3] = {0, 0, 0};
-  const bool visible = in_range && radii[idx] > 0;
+  const bool visible = in_range && my_radius > 0;
 
   if (visible) {
+    if (sh_staged) {
+      const float4* g4 = reinterpret_cast<const float4*>(shs + i * 48);
+      float4* s4 = reinterpret_cast<float4*>(s_tile);
+#pragma unroll
+      for (int k = 0; k < 12; k++)
+        if (k < sh_nq) {
+          const unsigned sa = (unsigned)__cvta_generic_to_shared(&s4[k * GB_THREADS + threadIdx.x]);
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(g4 + k));
+        }
+      asm volatile("cp.async.commit_group;\n" ::);
+    }
     const float4* a4 = reinterpret_cast<const float4*>(acc + i * 16);
     const float4 A0 = a4[0], A1 = a4[1], A2 = a4[2], A3 = a4[3];
+    const float4 rec1 = *reinterpret_cast<const float4*>(rec + i * REC_FLOATS + 4);    // con.z, opacity*coef, depth
+    const float4 rec2 = *reinterpret_cast<const float4*>(rec + i * REC_FLOATS + 8);    // r, g, b, nx
+    const float4 rec3 = *reinterpret_cast<const float4*>(rec + i * REC_FLOATS + 12);   // ny, nz
     o_color[0] = A0.x; o_color[1] = A0.y; o_color[2] = A0.z; o_depth = A0.w;
     o_norm[0] = A1.x; o_norm[1] = A1.y; o_norm[2] = A1.z;
     o_mean2D[0] = A1.w; o_mean2D[1] = A2.x; o_mean2D[2] = A2.y;
     o_conic[0] = A2.z; o_conic[1] = A2.w; o_conic[3] = A3.x;
     o_opac = A3.y;
 
-    const float mx = means3D[3 * i], my = means3D[3 * i + 1], mz = means3D[3 * i + 2];
     const float* cov3D = cov3Ds + 6 * i;
-    const float combined_opacity = rec[i * REC_FLOATS + REC_OPAC];
+    const float combined_opacity = rec1.y;
 
     // ---------------- conic -> cov2D -> cov3D, t (computeCov2DCUDA) ----------------
     {
@@ -191,73 +223,79 @@ gauss_bwd_kernel(int P, int D, int M, const float* __restrict__ means3D, const i
       const float ox = mx - campos[0], oy = my - campos[1], oz = mz - campos[2];
       const float len = sqrt(ox * ox + oy * oy + oz * oz);
       const float x = ox / len, y = oy / len, z = oz / len;
-      const unsigned cm = clamped[idx];
       dL_dRGB[0] = o_color[0] * ((cm & 1u) ? 0 : 1);
       dL_dRGB[1] = o_color[1] * ((cm & 2u) ? 0 : 1);
       dL_dRGB[2] = o_color[2] * ((cm & 4u) ? 0 : 1);
-      const float* sh = shs + i * M * 3;
-      float dRGBdx[3] = {0, 0, 0}, dRGBdy[3] = {0, 0, 0}, dRGBdz[3] = {0, 0, 0};
-      dsh_scale[0] = SH_C0;
-      if (D > 0) {
-        dsh_scale[1] = -SH_C1 * y; dsh_scale[2] = SH_C1 * z; dsh_scale[3] = -SH_C1 * x;
-#pragma unroll
-        for (int ch = 0; ch < 3; ch++) {
-          dRGBdx[ch] = -SH_C1 * sh[3 * 3 + ch];
-          dRGBdy[ch] = -SH_C1 * sh[1 * 3 + ch];
-          dRGBdz[ch] = SH_C1 * sh[2 * 3 + ch];
-        }
-        if (D > 1) {
-          const float xx = x * x, yy = y * y, zz = z * z;
-          const float xy = x * y, yz = y * z, xz = x * z;
-          dsh_scale[4] = SH_C2_0 * xy; dsh_scale[5] = SH_C2_1 * yz; dsh_scale[6] = SH_C2_2 * (2.f * zz - xx - yy);
-          dsh_scale[7] = SH_C2_3 * xz; dsh_scale[8] = SH_C2_4 * (xx - yy);
-#pragma unroll
+      auto sh_adjoint = [&](auto sh) {
+        float dRGBdx[3] = {0, 0, 0}, dRGBdy[3] = {0, 0, 0}, dRGBdz[3] = {0, 0, 0};
+        dsh_scale[0] = SH_C0;
+        if (D > 0) {
+          dsh_scale[1] = -SH_C1 * y; dsh_scale[2] = SH_C1 * z; dsh_scale[3] = -SH_C1 * x;
+  #pragma unroll
           for (int ch = 0; ch < 3; ch++) {
-            const float s4 = sh[4 * 3 + ch], s5 = sh[5 * 3 + ch], s6 = sh[6 * 3 + ch], s7 = sh[7 * 3 + ch], s8 = sh[8 * 3 + ch];
-            dRGBdx[ch] += SH_C2_0 * y * s4 + SH_C2_2 * 2.f * -x * s6 + SH_C2_3 * z * s7 + SH_C2_4 * 2.f * x * s8;
-            dRGBdy[ch] += SH_C2_0 * x * s4 + SH_C2_1 * z * s5 + SH_C2_2 * 2.f * -y * s6 + SH_C2_4 * 2.f * -y * s8;
-            dRGBdz[ch] += SH_C2_1 * y * s5 + SH_C2_2 * 2.f * 2.f * z * s6 + SH_C2_3 * x * s7;
+            dRGBdx[ch] = -SH_C1 * sh(3 * 3 + ch);
+            dRGBdy[ch] = -SH_C1 * sh(1 * 3 + ch);
+            dRGBdz[ch] = SH_C1 * sh(2 * 3 + ch);
           }
-          if (D > 2) {
-            dsh_scale[9] = SH_C3_0 * y * (3.f * xx - yy);
-            dsh_scale[10] = SH_C3_1 * xy * z;
-            dsh_scale[11] = SH_C3_2 * y * (4.f * zz - xx - yy);
-            dsh_scale[12] = SH_C3_3 * z * (2.f * zz - 3.f * xx - 3.f * yy);
-            dsh_scale[13] = SH_C3_4 * x * (4.f * zz - xx - yy);
-            dsh_scale[14] = SH_C3_5 * z * (xx - yy);
-            dsh_scale[15] = SH_C3_6 * x * (xx - 3.f * yy);
-#pragma unroll
+          if (D > 1) {
+            const float xx = x * x, yy = y * y, zz = z * z;
+            const float xy = x * y, yz = y * z, xz = x * z;
+            dsh_scale[4] = SH_C2_0 * xy; dsh_scale[5] = SH_C2_1 * yz; dsh_scale[6] = SH_C2_2 * (2.f * zz - xx - yy);
+            dsh_scale[7] = SH_C2_3 * xz; dsh_scale[8] = SH_C2_4 * (xx - yy);
+  #pragma unroll
             for (int ch = 0; ch < 3; ch++) {
-              const float s9 = sh[9 * 3 + ch], s10 = sh[10 * 3 + ch], s11 = sh[11 * 3 + ch], s12 = sh[12 * 3 + ch];
-              const float s13 = sh[13 * 3 + ch], s14 = sh[14 * 3 + ch], s15 = sh[15 * 3 + ch];
-              dRGBdx[ch] += (SH_C3_0 * s9 * 3.f * 2.f * xy + SH_C3_1 * s10 * yz + SH_C3_2 * s11 * -2.f * xy +
-                             SH_C3_3 * s12 * -3.f * 2.f * xz + SH_C3_4 * s13 * (-3.f * xx + 4.f * zz - yy) +
-                             SH_C3_5 * s14 * 2.f * xz + SH_C3_6 * s15 * 3.f * (xx - yy));
-              dRGBdy[ch] += (SH_C3_0 * s9 * 3.f * (xx - yy) + SH_C3_1 * s10 * xz +
-                             SH_C3_2 * s11 * (-3.f * yy + 4.f * zz - xx) + SH_C3_3 * s12 * -3.f * 2.f * yz +
-                             SH_C3_4 * s13 * -2.f * xy + SH_C3_5 * s14 * -2.f * yz + SH_C3_6 * s15 * -3.f * 2.f * xy);
-              dRGBdz[ch] += (SH_C3_1 * s10 * xy + SH_C3_2 * s11 * 4.f * 2.f * yz +
-                             SH_C3_3 * s12 * 3.f * (2.f * zz - xx - yy) + SH_C3_4 * s13 * 4.f * 2.f * xz +
-                             SH_C3_5 * s14 * (xx - yy));
+              const float s4 = sh(4 * 3 + ch), s5 = sh(5 * 3 + ch), s6 = sh(6 * 3 + ch), s7 = sh(7 * 3 + ch), s8 = sh(8 * 3 + ch);
+              dRGBdx[ch] += SH_C2_0 * y * s4 + SH_C2_2 * 2.f * -x * s6 + SH_C2_3 * z * s7 + SH_C2_4 * 2.f * x * s8;
+              dRGBdy[ch] += SH_C2_0 * x * s4 + SH_C2_1 * z * s5 + SH_C2_2 * 2.f * -y * s6 + SH_C2_4 * 2.f * -y * s8;
+              dRGBdz[ch] += SH_C2_1 * y * s5 + SH_C2_2 * 2.f * 2.f * z * s6 + SH_C2_3 * x * s7;
+            }
+            if (D > 2) {
+              dsh_scale[9] = SH_C3_0 * y * (3.f * xx - yy);
+              dsh_scale[10] = SH_C3_1 * xy * z;
+              dsh_scale[11] = SH_C3_2 * y * (4.f * zz - xx - yy);
+              dsh_scale[12] = SH_C3_3 * z * (2.f * zz - 3.f * xx - 3.f * yy);
+              dsh_scale[13] = SH_C3_4 * x * (4.f * zz - xx - yy);
+              dsh_scale[14] = SH_C3_5 * z * (xx - yy);
+              dsh_scale[15] = SH_C3_6 * x * (xx - 3.f * yy);
+  #pragma unroll
+              for (int ch = 0; ch < 3; ch++) {
+                const float s9 = sh(9 * 3 + ch), s10 = sh(10 * 3 + ch), s11 = sh(11 * 3 + ch), s12 = sh(12 * 3 + ch);
+                const float s13 = sh(13 * 3 + ch), s14 = sh(14 * 3 + ch), s15 = sh(15 * 3 + ch);
+                dRGBdx[ch] += (SH_C3_0 * s9 * 3.f * 2.f * xy + SH_C3_1 * s10 * yz + SH_C3_2 * s11 * -2.f * xy +
+                               SH_C3_3 * s12 * -3.f * 2.f * xz + SH_C3_4 * s13 * (-3.f * xx + 4.f * zz - yy) +
+                               SH_C3_5 * s14 * 2.f * xz + SH_C3_6 * s15 * 3.f * (xx - yy));
+                dRGBdy[ch] += (SH_C3_0 * s9 * 3.f * (xx - yy) + SH_C3_1 * s10 * xz +
+                               SH_C3_2 * s11 * (-3.f * yy + 4.f * zz - xx) + SH_C3_3 * s12 * -3.f * 2.f * yz +
+                               SH_C3_4 * s13 * -2.f * xy + SH_C3_5 * s14 * -2.f * yz + SH_C3_6 * s15 * -3.f * 2.f * xy);
+                dRGBdz[ch] += (SH_C3_1 * s10 * xy + SH_C3_2 * s11 * 4.f * 2.f * yz +
+                               SH_C3_3 * s12 * 3.f * (2.f * zz - xx - yy) + SH_C3_4 * s13 * 4.f * 2.f * xz +
+                               SH_C3_5 * s14 * (xx - yy));
+              }
             }
           }
         }
+        float3 dL_ddir;
+        dL_ddir.x = dRGBdx[0] * dL_dRGB[0] + dRGBdx[1] * dL_dRGB[1] + dRGBdx[2] * dL_dRGB[2];
+        dL_ddir.y = dRGBdy[0] * dL_dRGB[0] + dRGBdy[1] * dL_dRGB[1] + dRGBdy[2] * dL_dRGB[2];
+        dL_ddir.z = dRGBdz[0] * dL_dRGB[0] + dRGBdz[1] * dL_dRGB[1] + dRGBdz[2] * dL_dRGB[2];
+        const float3 dm = dnormvdv3(make_float3(ox, oy, oz), dL_ddir);
+        o_mean[0] += dm.x; o_mean[1] += dm.y; o_mean[2] += dm.z;
+      };
+      if (sh_staged) {
+        asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+        const float* sf = s_tile + 4 * threadIdx.x;   // coefficient j = word (j & 3) of float4 [j >> 2][t]
+        sh_adjoint([&](int j) { return sf[(j >> 2) * (4 * GB_THREADS) + (j & 3)]; });
+      } else {
+        const float* shg = shs + i * M * 3;
+        sh_adjoint([&](int j) { return shg[j]; });
       }
-      float3 dL_ddir;
-      dL_ddir.x = dRGBdx[0] * dL_dRGB[0] + dRGBdx[1] * dL_dRGB[1] + dRGBdx[2] * dL_dRGB[2];
-      dL_ddir.y = dRGBdy[0] * dL_dRGB[0] + dRGBdy[1] * dL_dRGB[1] + dRGBdy[2] * dL_dRGB[2];
-      dL_ddir.z = dRGBdz[0] * dL_dRGB[0] + dRGBdz[1] * dL_dRGB[1] + dRGBdz[2] * dL_dRGB[2];
-      const float3 dm = dnormvdv3(make_float3(ox, oy, oz), dL_ddir);
-      o_mean[0] += dm.x; o_mean[1] += dm.y; o_mean[2] += dm.z;
     }
 
     // ---------------- cov3D -> scale / rotation, normal -> rotation ----------------
     if (scales != nullptr) {
-      const float4 q = *reinterpret_cast<const float4*>(rotations + 4 * i);
-      const float r = q.x, x = q.y, y = q.z, z = q.w;
+      const float r = q_in.x, x = q_in.y, y = q_in.z, z = q_in.w;
       float R[3][3];
       rot_from_quat(r, x, y, z, R);
-      const float scx = scales[3 * i], scy = scales[3 * i + 1], scz = scales[3 * i + 2];
       const float s[3] = {scale_modifier * scx, scale_modifier * scy, scale_modifier * scz};
       float Mm[3][3];   // M = S * R : M[c][r] = s[r] * R[c][r]
 #pragma unroll
@@ -294,7 +332,7 @@ gauss_bwd_kernel(int P, int D, int M, const float* __restrict__ means3D, const i
         if (scx > scz && scy > scz) { ax0 = 0.f; ax1 = 0.f; ax2 = 1.f; }
         else if (scx > scy && scz > scy) { ax0 = 0.f; ax1 = 1.f; ax2 = 0.f; }
         else { ax0 = 1.f; ax1 = 0.f; ax2 = 0.f; }
-        const float n3x = rec[i * REC_FLOATS + REC_NX], n3y = rec[i * REC_FLOATS + REC_NY], n3z = rec[i * REC_FLOATS + REC_NZ];
+        const float n3x = rec2.w, n3y = rec3.x, n3z = rec3.y;
         // R * axis : out[r] = R[0][r]*ax0 + R[1][r]*ax1 + R[2][r]*ax2
         const float rn0 = R[0][0] * ax0 + R[1][0] * ax1 + R[2][0] * ax2;
         const float rn1 = R[0][1] * ax0 + R[1][1] * ax1 + R[2][1] * ax2;
@@ -319,8 +357,6 @@ gauss_bwd_kernel(int P, int D, int M, const float* __restrict__ means3D, const i
   // ---------------- write every output exactly once, coalesced ----------------
   // Per-thread stores of 3/4/6/48-float rows are strided across the warp (20 sectors per request measured);
   // stage the block's rows in shared memory and stream each output array out as contiguous 16-byte stores.
-  __shared__ __align__(16) float s_out[GB_THREADS * 31];
-  __shared__ __align__(128) float s_tile[WRITE_SH ? GB_THREADS * 48 : 4];   // 24 KB SH-gradient tile for the bulk store
   float* s_sh = s_tile;   // the generic (M != 16 / unaligned) path keeps 19 floats per Gaussian here instead
   const bool use_tma = WRITE_SH && M == 16 && (reinterpret_cast<uintptr_t>(dL_dsh) & 15) == 0;
   const int t = threadIdx.x;
@@ -348,6 +384,7 @@ gauss_bwd_kernel(int P, int D, int M, const float* __restrict__ means3D, const i
   s_scale[3 * t] = o_scale[0]; s_scale[3 * t + 1] = o_scale[1]; s_scale[3 * t + 2] = o_scale[2];
   *reinterpret_cast<float4*>(s_rot + 4 * t) = make_float4(o_rot[0], o_rot[1], o_rot[2], o_rot[3]);
   if (WRITE_SH && !use_tma) {
+    __syncthreads();   // s_tile may still hold other threads' staged SH coefficients
 #pragma unroll
     for (int k = 0; k < 16; k++) s_sh[19 * t + k] = dsh_scale[k];
     s_sh[19 * t + 16] = dL_dRGB[0]; s_sh[19 * t + 17] = dL_dRGB[1]; s_sh[19 * t + 18] = dL_dRGB[2];

@@ -172,7 +172,7 @@ __device__ __forceinline__ void sh_to_rgb(int deg, const float* __restrict__ sh 
 
 constexpr int PRE_THREADS = 256;
 
-__global__ void __launch_bounds__(PRE_THREADS)
+__global__ void __launch_bounds__(PRE_THREADS, 3)
 preprocess_kernel(int P, int D, int M,
                   const float* __restrict__ means3D, const float* __restrict__ scales, float scale_modifier,
                   const float* __restrict__ rotations, const float* __restrict__ opacities,
@@ -191,28 +191,59 @@ preprocess_kernel(int P, int D, int M,
   TileRect vis_rect = {0, 0, 0, 0};
   float vis_depth = 0.f;
 
+  extern __shared__ __align__(16) unsigned char pre_smem[];
+  float4* s_sh = reinterpret_cast<float4*>(pre_smem);                                    // [12][PRE_THREADS]
+  uint32_t* s_incl = reinterpret_cast<uint32_t*>(pre_smem + 12 * PRE_THREADS * sizeof(float4));
+  int4* s_rect = reinterpret_cast<int4*>(pre_smem + 12 * PRE_THREADS * sizeof(float4) + PRE_THREADS * sizeof(uint32_t));
+
+  // Every per-Gaussian input that does not depend on the cull is requested up front, so the kernel pays one
+  // DRAM latency instead of one per dependent branch (the kernel is latency-, not bandwidth-bound).
   const float px = means3D[3 * idx], py = means3D[3 * idx + 1], pz = means3D[3 * idx + 2];
+  const bool need_sr = cov3D_precomp == nullptr || norm3D_precomp == nullptr;
+  float sx = 0.f, sy = 0.f, sz = 0.f;
+  float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (need_sr) {
+    sx = scales[3 * idx]; sy = scales[3 * idx + 1]; sz = scales[3 * idx + 2];
+    q = *reinterpret_cast<const float4*>(rotations + 4 * (size_t)idx);
+  }
+  const float opac_in = opacities[idx];
   const float* vm = viewmatrix;
   const float* pm = projmatrix;
+  // 192 contiguous, 16-byte aligned bytes of SH per Gaussian: staged by cp.async into this thread's own
+  // shared-memory column while the covariance math runs
+  const bool sh_staged = colors_precomp == nullptr && M == 16 && (reinterpret_cast<uintptr_t>(shs) & 15) == 0;
+  const int sh_nq = D == 0 ? 1 : (D == 1 ? 3 : (D == 2 ? 7 : 12));   // float4s covering (D+1)^2 coefficients
 
   int out_radius = 0;
   uint32_t out_tiles = 0;
 
   const float view_z = vm[2] * px + vm[6] * py + vm[10] * pz + vm[14];
+  bool sh_in_flight = false;
+  auto stage_sh = [&]() {
+    const float4* s4 = reinterpret_cast<const float4*>(shs + (size_t)idx * 48);
+#pragma unroll
+    for (int k = 0; k < 12; k++)
+      if (k < sh_nq) {
+        const unsigned sa = (unsigned)__cvta_generic_to_shared(&s_sh[k * PRE_THREADS + threadIdx.x]);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(s4 + k));
+      }
+    asm volatile("cp.async.commit_group;\n" ::);
+  };
   if (in_range && view_z > 0.2f) {
     const float hx = pm[0] * px + pm[4] * py + pm[8] * pz + pm[12];
     const float hy = pm[1] * px + pm[5] * py + pm[9] * pz + pm[13];
     const float hw = pm[3] * px + pm[7] * py + pm[11] * pz + pm[15];
     const float p_w = 1.0f / (hw + 0.0000001f);
     const float proj_x = hx * p_w, proj_y = hy * p_w;
+    // speculative: a centre within 1.25x of the image almost always ends up with a non-empty tile rectangle;
+    // anything the guess misses is staged later, anything it over-fetches is only wasted bandwidth
+    if (sh_staged && fabsf(proj_x) < 1.25f && fabsf(proj_y) < 1.25f) { stage_sh(); sh_in_flight = true; }
 
     Sym3 V;
     if (cov3D_precomp != nullptr) {
       const float* c = cov3D_precomp + 6 * (size_t)idx;
       V.c0 = c[0]; V.c1 = c[1]; V.c2 = c[2]; V.c3 = c[3]; V.c4 = c[4]; V.c5 = c[5];
     } else {
-      const float sx = scales[3 * idx], sy = scales[3 * idx + 1], sz = scales[3 * idx + 2];
-      const float4 q = *reinterpret_cast<const float4*>(rotations + 4 * (size_t)idx);
       V = cov3d_from_scale_rot(sx, sy, sz, scale_modifier, q.x, q.y, q.z, q.w);
       float* co = cov3D_out + 6 * (size_t)idx;
       co[0] = V.c0; co[1] = V.c1; co[2] = V.c2; co[3] = V.c3; co[4] = V.c4; co[5] = V.c5;
@@ -240,23 +271,20 @@ preprocess_kernel(int P, int D, int M,
         if (norm3D_precomp != nullptr) {
           n[0] = norm3D_precomp[3 * idx]; n[1] = norm3D_precomp[3 * idx + 1]; n[2] = norm3D_precomp[3 * idx + 2];
         } else {
-          const float sx = scales[3 * idx], sy = scales[3 * idx + 1], sz = scales[3 * idx + 2];
-          const float4 q = *reinterpret_cast<const float4*>(rotations + 4 * (size_t)idx);
           normal_from_scale_rot(sx, sy, sz, q.x, q.y, q.z, q.w, px, py, pz, cam_pos[0], cam_pos[1], cam_pos[2], n);
         }
         float rgb[3];
         unsigned cmask = 0;
         if (colors_precomp == nullptr) {
           const float* shp = shs + (size_t)idx * M * 3;
-          if (M == 16 && (reinterpret_cast<uintptr_t>(shs) & 15) == 0) {
-            // 192 contiguous, 16-byte aligned bytes per Gaussian: twelve 128-bit loads instead of 48 scalar ones
+          if (sh_staged) {
             float shl[48];
-            const float4* s4 = reinterpret_cast<const float4*>(shp);
-            const int nq = D == 0 ? 1 : (D == 1 ? 3 : (D == 2 ? 7 : 12));   // float4s covering (D+1)^2 coefficients
+            if (!sh_in_flight) stage_sh();
+            asm volatile("cp.async.wait_group 0;\n" ::: "memory");
 #pragma unroll
             for (int k = 0; k < 12; k++) {
               float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (k < nq) v = __ldg(s4 + k);
+              if (k < sh_nq) v = s_sh[k * PRE_THREADS + threadIdx.x];
               shl[4 * k] = v.x; shl[4 * k + 1] = v.y; shl[4 * k + 2] = v.z; shl[4 * k + 3] = v.w;
             }
             sh_to_rgb(D, shl, px, py, pz, cam_pos[0], cam_pos[1], cam_pos[2], rgb, cmask);
@@ -270,7 +298,7 @@ preprocess_kernel(int P, int D, int M,
 
         float4* o = reinterpret_cast<float4*>(rec + (size_t)idx * REC_FLOATS);
         o[0] = make_float4(pix_x, pix_y, conx, cony);
-        o[1] = make_float4(conz, opacities[idx] * cov.w, view_z, 0.f);
+        o[1] = make_float4(conz, opac_in * cov.w, view_z, 0.f);
         o[2] = make_float4(rgb[0], rgb[1], rgb[2], n[0]);
         o[3] = make_float4(n[1], n[2], 0.f, 0.f);
         out_radius = iradius;
@@ -291,8 +319,7 @@ preprocess_kernel(int P, int D, int M,
   // shared memory), so a large splat no longer serialises its lane and 32 independent histogram
   // atomics are in flight per step.  The histogram atomic (it replaces the per-Gaussian prefix sum of
   // the reference) hands back the instance's slot inside its tile bucket: the later scatter needs none.
-  __shared__ uint32_t s_incl[PRE_THREADS];
-  __shared__ int4 s_rect[PRE_THREADS];      // x0, y0, width, depth bits
+  asm volatile("cp.async.wait_group 0;\n" ::: "memory");   // culled threads may still have copies in flight
   const unsigned lane = threadIdx.x & 31u;
   const unsigned wbase = threadIdx.x & ~31u;
   uint32_t incl = out_tiles;
@@ -306,21 +333,37 @@ preprocess_kernel(int P, int D, int M,
   s_incl[threadIdx.x] = incl;
   s_rect[threadIdx.x] = make_int4(vis_rect.x0, vis_rect.y0, vis_rect.x1 - vis_rect.x0, (int)__float_as_uint(vis_depth));
   __syncwarp();
-  for (uint32_t j = lane; j < warp_total; j += 32) {
-    // owner = first lane whose inclusive prefix exceeds j
-    int lo = 0;
+  // four instances per lane and step, so four histogram atomics are in flight before the first result is needed
+  constexpr int APP = 4;
+  for (uint32_t j0 = lane; j0 < warp_total; j0 += 32 * APP) {
+    uint32_t t[APP], gid[APP], dep[APP], pos[APP];
 #pragma unroll
-    for (int step = 16; step > 0; step >>= 1)
-      if (s_incl[wbase + lo + step - 1] <= j) lo += step;
-    const uint32_t excl = lo > 0 ? s_incl[wbase + lo - 1] : 0u;
-    const int4 rc = s_rect[wbase + lo];
-    const uint32_t k = j - excl;                       // k-th tile of the owner's rectangle, row-major
-    const uint32_t ty = k / (uint32_t)rc.z, tx = k - ty * (uint32_t)rc.z;
-    const uint32_t t = (uint32_t)(rc.y + (int)ty) * (uint32_t)gx + (uint32_t)(rc.x + (int)tx);
-    const uint32_t pos = atomicAdd(&tile_count[t], 1u);
-    const unsigned long long slot = (unsigned long long)warp_base + j;
-    const uint32_t gid = (uint32_t)(blockIdx.x * PRE_THREADS) + wbase + (uint32_t)lo;
-    if (slot < capacity) tmp[slot] = make_uint4(gid, (uint32_t)rc.w, t, pos);
+    for (int u = 0; u < APP; u++) {
+      const uint32_t j = j0 + 32u * u;
+      t[u] = 0xffffffffu;
+      if (j < warp_total) {
+        // owner = first lane whose inclusive prefix exceeds j
+        int lo = 0;
+#pragma unroll
+        for (int step = 16; step > 0; step >>= 1)
+          if (s_incl[wbase + lo + step - 1] <= j) lo += step;
+        const uint32_t excl = lo > 0 ? s_incl[wbase + lo - 1] : 0u;
+        const int4 rc = s_rect[wbase + lo];
+        const uint32_t k = j - excl;                       // k-th tile of the owner's rectangle, row-major
+        const uint32_t ty = k / (uint32_t)rc.z, tx = k - ty * (uint32_t)rc.z;
+        t[u] = (uint32_t)(rc.y + (int)ty) * (uint32_t)gx + (uint32_t)(rc.x + (int)tx);
+        gid[u] = (uint32_t)(blockIdx.x * PRE_THREADS) + wbase + (uint32_t)lo;
+        dep[u] = (uint32_t)rc.w;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < APP; u++)
+      if (t[u] != 0xffffffffu) pos[u] = atomicAdd(&tile_count[t[u]], 1u);
+#pragma unroll
+    for (int u = 0; u < APP; u++) {
+      const unsigned long long slot = (unsigned long long)warp_base + j0 + 32u * u;
+      if (t[u] != 0xffffffffu && slot < capacity) tmp[slot] = make_uint4(gid[u], dep[u], t[u], pos[u]);
+    }
   }
 }
 
@@ -339,8 +382,14 @@ void sfgs_launch_preprocess(const sfgs_forward_args* a, const GeomLayout& g, con
                             const BinningLayout& b, unsigned long long capacity, float focal_x, float focal_y,
                             cudaStream_t st) {
   const int blocks = (a->P + PRE_THREADS - 1) / PRE_THREADS;
+  constexpr size_t smem = PRE_THREADS * (12 * sizeof(float4) + sizeof(uint32_t) + sizeof(int4));
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(preprocess_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr_set = true;
+  }
   SFGS_COUNT_LAUNCH();
-  preprocess_kernel<<<blocks, PRE_THREADS, 0, st>>>(
+  preprocess_kernel<<<blocks, PRE_THREADS, smem, st>>>(
       a->P, a->D, a->M, a->means3D, a->scales, a->scale_modifier, a->rotations, a->opacities, a->shs,
       a->cov3D_precomp, a->norm3D_precomp, a->colors_precomp, a->viewmatrix, a->projmatrix, a->cam_pos,
       a->width, a->height, a->tan_fovx, a->tan_fovy, focal_x, focal_y, a->kernel_size, im.tiles_x, im.tiles_y,

@@ -205,6 +205,7 @@ render_bwd_kernel(const uint2* __restrict__ ranges, const char* __restrict__ bin
     __syncwarp();
   };
 
+  const unsigned cparam_addr = (unsigned)__cvta_generic_to_shared(&S.cparam[wid][0][0]) + (unsigned)(lane & 1) * 16u;
   issue(0, 0);
   int kcur = 0;   // fill level of this warp's chunk; persists across batches
   for (int b = 0; b < nbatches; b++) {
@@ -240,9 +241,12 @@ render_bwd_kernel(const uint2* __restrict__ ranges, const char* __restrict__ bin
           const float inv_1ma = __frcp_rn(1.f - alpha);   // shared by the T recovery and the background term
           T = T * inv_1ma;
           const float weight = alpha * T;
-          float g = rc.x * dLc0;
-          g += rc.y * dLc1; g += rc.z * dLc2; g += rb.z * dLd;
-          g += rc.w * dLn0; g += rd.x * dLn1; g += rd.y * dLn2; g += dLa;
+          // two independent chains: halves the dependent-FMA latency of the dot product
+          float g = rc.x * dLc0, g2 = rc.w * dLn0;
+          g += rc.y * dLc1; g2 += rd.x * dLn1;
+          g += rc.z * dLc2; g2 += rd.y * dLn2;
+          g += rb.z * dLd;  g2 += dLa;
+          g += g2;
           A = last_alpha * g_last + (1.f - last_alpha) * A;
           g_last = g;
           float dL_dalpha = g - A;
@@ -263,8 +267,18 @@ render_bwd_kernel(const uint2* __restrict__ ranges, const char* __restrict__ bin
           h_out = G * dL_dalpha;
         }
         S.wh[wid][lane][kcur] = make_float2(w_out, h_out);
-        if (lane == 0) S.cparam[wid][kcur][0] = ra;
-        if (lane == 1) S.cparam[wid][kcur][1] = make_float4(rb.x, rb.y, __uint_as_float(S.id[stage][e]), 0.f);
+        {
+          // lanes 0 and 1 park the record's parameters with the chunk slot: select + one predicated store, no branch
+          const float idf = __uint_as_float(S.id[stage][e]);
+          asm volatile(
+              "{\n\t.reg .pred p0, p2;\n\t.reg .f32 a, b, c, d;\n\t"
+              "setp.eq.u32 p0, %0, 0;\n\tsetp.lt.u32 p2, %0, 2;\n\t"
+              "selp.f32 a, %2, %6, p0;\n\tselp.f32 b, %3, %7, p0;\n\tselp.f32 c, %4, %8, p0;\n\tselp.f32 d, %5, 0f00000000, p0;\n\t"
+              "@p2 st.shared.v4.f32 [%1], {a, b, c, d};\n\t}\n" ::"r"(lane),
+              "r"(cparam_addr + (unsigned)kcur * 32u), "f"(ra.x), "f"(ra.y), "f"(ra.z), "f"(ra.w), "f"(rb.x), "f"(rb.y),
+              "f"(idf)
+              : "memory");
+        }
         if (++kcur == CH) { phase2(CH); kcur = 0; }
       }
     }
