@@ -203,23 +203,24 @@ def timed_steps(step_fn, steps, warmup, flush, dev, between=None):
     return ms
 
 
-def measure(step_fn, steps, warmup, flush, dev, between=None, max_attempts=3):
-    """Time exactly `steps` steps; a pass disturbed by the host is rejected and re-measured (at most twice).
+def measure(step_fn, steps, warmup, flush, dev, between=None, max_attempts=5):
+    """Time exactly `steps` steps; a pass disturbed from outside is rejected and re-measured.
 
     Every step launches ~10 kernels from Python and the forward waits once for the instance count, so a host
-    core that is descheduled for a few ms leaves the GPU idle inside the timed step.  On the shared boxes this
-    shows up as whole passes whose median step is 2-4x the pass minimum (observed on either leg, at random).
-    A pass counts as clean when its median is within 15 % of its fastest step; the reported pass is the first
-    clean one, or the pass with the smallest total if none is.  All attempts are listed in the JSON line."""
+    core that is descheduled for a few ms leaves the GPU idle inside the timed step; the boxes are shared
+    (load average 40-60 on 128 cores observed) and single steps of 5-250 ms appear at random in either leg.
+    A pass counts as clean when its MEAN step is within 10 % of its fastest step (one large spike is enough to
+    fail it); the reported pass is the first clean one, or the pass with the smallest total if none of
+    `max_attempts` is.  Every attempt is listed in the JSON line."""
     attempts = []
     for k in range(max_attempts):
         ms = timed_steps(step_fn, steps, warmup if k == 0 else 3, flush, dev, between)
-        srt = sorted(ms)
         attempts.append(ms)
-        if srt[len(srt) // 2] <= 1.15 * srt[0]:
+        if sum(ms) / len(ms) <= 1.10 * min(ms):
             break
-    best = attempts[-1] if len(attempts) < max_attempts or sorted(attempts[-1])[len(ms) // 2] <= 1.15 * min(attempts[-1]) \
-        else min(attempts, key=sum)
+    best = min(attempts, key=sum)
+    if sum(attempts[-1]) / len(attempts[-1]) <= 1.10 * min(attempts[-1]):
+        best = attempts[-1]
     info = {"attempts": len(attempts), "ms_per_step_of_each_attempt": [round(sum(a) / len(a), 4) for a in attempts],
             "reported_min_ms": round(min(best), 4), "reported_median_ms": round(sorted(best)[len(best) // 2], 4)}
     return best, info
@@ -422,7 +423,7 @@ def main():
                    "d2h_bytes_per_step": 4},
            "clocks": clocks}
     out["timing"] = {"value": value_info, "e2e": e2e_info,
-                     "rule": "a pass whose median step exceeds 1.15x its fastest step is re-measured (<= 3 passes)"}
+                     "rule": "a pass whose mean step exceeds 1.10x its fastest step is re-measured (<= 5 passes)"}
     out["e2e"]["api"] = ("diff_gauss.GaussianRasterizer + autograd" if args.impl == "ours"
                          else "reference CudaRasterizer::Rasterizer forward/backward")
     if args.impl == "ours":
@@ -434,15 +435,19 @@ def main():
         R, V = int(f[0]), int((f[5] > 0).sum().item())
         M = (SH_DEGREE + 1) ** 2
         tiles = ((cam.width + 15) // 16) * ((cam.height + 15) // 16)
-        native.profile_enable(True)
+        # per-stage CUDA-event times, one read per step; the MEDIAN over the steps is reported (the boxes are
+        # shared: a mean is ruined by one step that was disturbed)
+        per_stage = {}
         for _ in range(steps):
             flush()
+            native.profile_enable(True)
             step()
-        torch.cuda.synchronize(dev)
-        prof = native.profile_read()
+            torch.cuda.synchronize(dev)
+            for k, v in native.profile_read().items():
+                per_stage.setdefault(k, []).append(v[0] / v[1] if v[1] else 0.0)
         native.profile_enable(False)
         alg = algorithmic_bytes(scene.P, V, R, N, M, tiles)
-        stage_ms = {k: (v[0] / v[1] if v[1] else 0.0) for k, v in prof.items()}
+        stage_ms = {k: float(np.median(v)) for k, v in per_stage.items()}
         dom = max((k for k in stage_ms if k in alg), key=lambda k: stage_ms[k])
         peak, peak_src = peaks()
         ach = alg[dom] / (stage_ms[dom] / 1e3) / 1e9

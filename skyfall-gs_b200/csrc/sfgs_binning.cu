@@ -96,24 +96,45 @@ scatter_keys_kernel(const uint4* __restrict__ tmp, const uint2* __restrict__ ran
 // One CTA per tile, two launches over the same grid: a light variant (128 threads, 1024-key window) for
 // the common short lists and a heavy one (256 threads, 4096-key window, global radix fallback beyond that);
 // a CTA whose tile belongs to the other class exits at once.  Lists inside the window are sorted with a
-// bitonic network on 64-bit (depth_bits << 32 | id) keys padded with ~0.
+// Bitonic network on the n 64-bit (depth_bits << 32 | id) keys of one tile, n2 = next power of two >= n.
+//
+// The network is the "all comparators ascending" form: round k first pairs element t of every k-block with its
+// mirror k-1-t, then runs the usual strides k/4 .. 1.  With every comparator ascending, keys at positions >= n
+// behave as +inf that never move, so a comparator whose upper index is >= n is simply skipped: nothing is padded
+// and the work per stage is ~n/2 exchanges instead of n2/2 (tiles average ~280 keys, i.e. n2 = 512).
+//
+// Exchange i of a stage touches two keys of the aligned 2*j-block that contains 2*i (j = k/2 for the mirror
+// stage).  For j <= 32 the 32 exchanges of one warp stay inside one aligned 64-key block, so consecutive stages
+// with j <= 32 only need __syncwarp(); block-wide barriers remain for the strides j >= 64.
 template <int THREADS>
-__device__ __forceinline__ void bitonic_smem(uint64_t* s, int n2) {
-  // Compare-exchange i of a stage touches lo = ((i & ~(j-1)) << 1) | (i & (j-1)) and hi = lo | j.  For j <= 32 the
-  // 32 exchanges of one warp stay inside one aligned 64-key block, so consecutive stages with j <= 32 only need
-  // __syncwarp(); block-wide barriers remain only for the strides j >= 64 (6 instead of 45 barriers at n2 = 512).
+__device__ __forceinline__ void bitonic_smem(uint64_t* s, int n, int n2) {
   const int half = n2 >> 1;
   for (int k = 2; k <= n2; k <<= 1) {
     for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int i = threadIdx.x; i < half; i += THREADS) {
-        const int lo = ((i & ~(j - 1)) << 1) | (i & (j - 1));
-        const int hi = lo | j;
-        const uint64_t a = s[lo], b = s[hi];
-        const bool up = ((lo & k) == 0);
-        if ((a > b) == up) { s[lo] = b; s[hi] = a; }
+      if (j == (k >> 1)) {
+        const int lim = min(half, (n >> 1) + (k >> 2) + 1);   // exchanges beyond this have hi >= n
+        for (int i = threadIdx.x; i < lim; i += THREADS) {
+          const int t = i & (j - 1);
+          const int blk = (i - t) << 1;                        // first key of the k-block
+          const int lo = blk + t, hi = blk + k - 1 - t;
+          if (hi < n) {
+            const uint64_t a = s[lo], b = s[hi];
+            if (a > b) { s[lo] = b; s[hi] = a; }
+          }
+        }
+      } else {
+        const int lim = min(half, (n + 1) >> 1);
+        for (int i = threadIdx.x; i < lim; i += THREADS) {
+          const int lo = ((i & ~(j - 1)) << 1) | (i & (j - 1));
+          const int hi = lo | j;
+          if (hi < n) {
+            const uint64_t a = s[lo], b = s[hi];
+            if (a > b) { s[lo] = b; s[hi] = a; }
+          }
+        }
       }
-      // the next stage has stride j/2: it is warp-local iff j/2 <= 32, and this stage's writes came from the
-      // same warp iff j <= 32
+      // the next stage has stride j/2 (or k for the next round's mirror stage): it is warp-local iff that stride
+      // is <= 32, and this stage's writes came from the same warp iff j <= 32
       if (j > 32 || (j == 1 && (k << 1) > 64 && k < n2)) __syncthreads();
       else __syncwarp();
     }
@@ -180,9 +201,9 @@ tile_sort_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
   uint64_t* bucket = keys + rg.x;
   if (n <= WINDOW) {
     int n2 = 2; while (n2 < n) n2 <<= 1;
-    for (int i = threadIdx.x; i < n2; i += THREADS) s[i] = (i < n) ? bucket[i] : ~0ull;
+    for (int i = threadIdx.x; i < n; i += THREADS) s[i] = bucket[i];
     __syncthreads();
-    bitonic_smem<THREADS>(s, n2);
+    bitonic_smem<THREADS>(s, n, n2);
     for (int i = threadIdx.x; i < n; i += THREADS) {
       const uint64_t k = s[i];
       bucket[i] = k;

@@ -7,13 +7,16 @@
 // torch::zeros fills of RasterizeGaussiansBackwardCUDA
 // (RAST/rasterize_points.cu:180-196): one thread per Gaussian reads the 14
 // blend-adjoint sums produced by the tile kernel, runs the whole chain in
-// registers and writes every output element exactly once (zeros for culled
-// Gaussians), so no output needs a prior memset.
+// registers; the block first zero-fills its span of every output array with
+// coalesced stores, so no output needs a prior memset, then only the visible
+// Gaussians — compacted into dense warps — run the adjoint chain and overwrite
+// their rows.
 #include "sfgs_common.cuh"
 
 namespace {
 
 constexpr int GB_THREADS = 128;
+constexpr int GB_SPAN = 256;   // Gaussians per block (two per thread in the cheap phases)
 
 __device__ __forceinline__ void rot_from_quat(float r, float x, float y, float z, float R[3][3]) {
   R[0][0] = 1.f - 2.f * (y * y + z * z); R[0][1] = 2.f * (x * y - r * z); R[0][2] = 2.f * (x * z + r * y);
@@ -45,51 +48,101 @@ gauss_bwd_kernel(int P, int D, int M, const float* __restrict__ means3D, const i
                  float* __restrict__ dL_dcolor, float* __restrict__ dL_ddepth, float* __restrict__ dL_dmean3D,
                  float* __restrict__ dL_dcov3D, float* __restrict__ dL_dnorm3D, float* __restrict__ dL_dsh,
                  float* __restrict__ dL_dscale, float* __restrict__ dL_drot) {
-  const int idx_raw = blockIdx.x * GB_THREADS + threadIdx.x;
-  const bool in_range = idx_raw < P;
-  const int idx = in_range ? idx_raw : P - 1;     // out-of-range threads idle through the math, join the block-wide store
-  const size_t i = (size_t)idx;
-
-  // shared memory: the output staging rows and one 24 KB tile that first receives this block's SH coefficients
-  // (cp.async, column t of a [12][128] float4 array) and later, after the block barrier, the SH-gradient rows
-  __shared__ __align__(16) float s_out[GB_THREADS * 31];
+  // 24 KB tile: column t of a [12][128] float4 array receives thread t's SH coefficients by cp.async
+  // (fast path), or 19 floats of per-thread scratch for the generic dL_dsh store
   __shared__ __align__(128) float s_tile[WRITE_SH ? GB_THREADS * 48 : 4];
+  __shared__ unsigned short s_list[GB_SPAN];
+  __shared__ int s_cnt[2 * GB_THREADS / 32];
+  const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+  const int base = blockIdx.x * GB_SPAN;
+  const int nspan = min(GB_SPAN, P - base);
 
-  // Everything that does not depend on the visibility test is requested before it: the kernel is bound by DRAM
-  // latency (ncu: long-scoreboard stalls, 30 % of HBM bandwidth), not by bytes.
-  const int my_radius = radii[idx];
-  const float mx = means3D[3 * i], my = means3D[3 * i + 1], mz = means3D[3 * i + 2];
-  float4 q_in = make_float4(0.f, 0.f, 0.f, 0.f);
-  float scx = 0.f, scy = 0.f, scz = 0.f;
-  if (scales != nullptr) {
-    q_in = *reinterpret_cast<const float4*>(rotations + 4 * i);
-    scx = scales[3 * i]; scy = scales[3 * i + 1]; scz = scales[3 * i + 2];
+  // ---------------- phase A: which Gaussians of the span were rasterized ----------------
+  // Culled Gaussians (64 % of the 1M-Gaussian benchmark frame) only need zeros.  Running the adjoint chain
+  // thread-per-Gaussian left 36 % of the lanes of every warp doing useful work; instead the visible ones are
+  // compacted (in index order) and processed by dense warps.
+  bool vis[2];
+  unsigned bal[2];
+#pragma unroll
+  for (int r = 0; r < 2; r++) {
+    const int g = r * GB_THREADS + t;
+    vis[r] = g < nspan && radii[base + g] > 0;
+    bal[r] = __ballot_sync(0xffffffffu, vis[r]);
+    if (lane == 0) s_cnt[r * (GB_THREADS / 32) + wid] = __popc(bal[r]);
   }
-  const unsigned cm = shs != nullptr ? clamped[idx] : 0u;
-  const bool sh_staged = WRITE_SH && shs != nullptr && M == 16 && (reinterpret_cast<uintptr_t>(shs) & 15) == 0;
+  __syncthreads();
+  int nvis = 0;
+#pragma unroll
+  for (int r = 0; r < 2; r++) {
+    const int seg = r * (GB_THREADS / 32) + wid;
+    int off = 0;
+#pragma unroll
+    for (int q = 0; q < 2 * GB_THREADS / 32; q++) off += q < seg ? s_cnt[q] : 0;
+    if (vis[r]) s_list[off + __popc(bal[r] & ((1u << lane) - 1u))] = (unsigned short)(r * GB_THREADS + t);
+  }
+#pragma unroll
+  for (int q = 0; q < 2 * GB_THREADS / 32; q++) nvis += s_cnt[q];
+
+  // every output row of the span starts as zeros: contiguous, 16-byte stores wherever the caller's buffer allows
+  if (nvis < nspan) {
+    auto zero_fill = [&](float* dst, int width) {
+      const int nfl = nspan * width;
+      float* d = dst + (size_t)base * width;
+      const int nv4 = ((reinterpret_cast<uintptr_t>(d) & 15) == 0) ? (nfl >> 2) : 0;
+      const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int i = t; i < nv4; i += GB_THREADS) reinterpret_cast<float4*>(d)[i] = z;
+      for (int i = (nv4 << 2) + t; i < nfl; i += GB_THREADS) d[i] = 0.f;
+    };
+    zero_fill(dL_dmean2D, 3);
+    zero_fill(dL_dconic, 4);
+    zero_fill(dL_dopacity, 1);
+    zero_fill(dL_dcolor, 3);
+    zero_fill(dL_ddepth, 1);
+    zero_fill(dL_dmean3D, 3);
+    zero_fill(dL_dcov3D, 6);
+    zero_fill(dL_dnorm3D, 3);
+    zero_fill(dL_dscale, 3);
+    zero_fill(dL_drot, 4);
+    if (WRITE_SH) zero_fill(dL_dsh, 3 * M);
+  }
+  __syncthreads();   // orders the zero fill before the row stores below, and publishes s_list
+
+  const bool sh_fast = WRITE_SH && shs != nullptr && M == 16 && (reinterpret_cast<uintptr_t>(shs) & 15) == 0 &&
+                       (reinterpret_cast<uintptr_t>(dL_dsh) & 15) == 0;
+  const bool sh_staged = sh_fast;
   const int sh_nq = D == 0 ? 1 : (D == 1 ? 3 : (D == 2 ? 7 : 12));   // float4s covering (D+1)^2 coefficients
 
-  float o_mean2D[3] = {0, 0, 0}, o_conic[4] = {0, 0, 0, 0}, o_opac = 0, o_color[3] = {0, 0, 0}, o_depth = 0;
-  float o_mean[3] = {0, 0, 0}, o_cov[6] = {0, 0, 0, 0, 0, 0}, o_norm[3] = {0, 0, 0};
-  float o_scale[3] = {0, 0, 0}, o_rot[4] = {0, 0, 0, 0};
-  float dsh_scale[16];   // dRGB/dsh_k for k < (D+1)^2, else 0
+  // ---------------- phase B: dense warps over the visible Gaussians ----------------
+  for (int k = t; k < nvis; k += GB_THREADS) {
+    const int idx = base + (int)s_list[k];
+    const size_t i = (size_t)idx;
+    float o_mean2D[3] = {0, 0, 0}, o_conic[4] = {0, 0, 0, 0}, o_opac = 0, o_color[3] = {0, 0, 0}, o_depth = 0;
+    float o_mean[3] = {0, 0, 0}, o_cov[6] = {0, 0, 0, 0, 0, 0}, o_norm[3] = {0, 0, 0};
+    float o_scale[3] = {0, 0, 0}, o_rot[4] = {0, 0, 0, 0};
+    float dsh_scale[16];   // dRGB/dsh_k for k < (D+1)^2, else 0
 #pragma unroll
-  for (int k = 0; k < 16; k++) dsh_scale[k] = 0.f;
-  float dL_dRGB[3] = {0, 0, 0};
-  const bool visible = in_range && my_radius > 0;
+    for (int q = 0; q < 16; q++) dsh_scale[q] = 0.f;
+    float dL_dRGB[3] = {0, 0, 0};
 
-  if (visible) {
     if (sh_staged) {
       const float4* g4 = reinterpret_cast<const float4*>(shs + i * 48);
       float4* s4 = reinterpret_cast<float4*>(s_tile);
 #pragma unroll
-      for (int k = 0; k < 12; k++)
-        if (k < sh_nq) {
-          const unsigned sa = (unsigned)__cvta_generic_to_shared(&s4[k * GB_THREADS + threadIdx.x]);
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(g4 + k));
+      for (int q = 0; q < 12; q++)
+        if (q < sh_nq) {
+          const unsigned sa = (unsigned)__cvta_generic_to_shared(&s4[q * GB_THREADS + threadIdx.x]);
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(g4 + q));
         }
       asm volatile("cp.async.commit_group;\n" ::);
     }
+    const float mx = means3D[3 * i], my = means3D[3 * i + 1], mz = means3D[3 * i + 2];
+    float4 q_in = make_float4(0.f, 0.f, 0.f, 0.f);
+    float scx = 0.f, scy = 0.f, scz = 0.f;
+    if (scales != nullptr) {
+      q_in = *reinterpret_cast<const float4*>(rotations + 4 * i);
+      scx = scales[3 * i]; scy = scales[3 * i + 1]; scz = scales[3 * i + 2];
+    }
+    const unsigned cm = shs != nullptr ? clamped[idx] : 0u;
     const float4* a4 = reinterpret_cast<const float4*>(acc + i * 16);
     const float4 A0 = a4[0], A1 = a4[1], A2 = a4[2], A3 = a4[3];
     const float4 rec1 = *reinterpret_cast<const float4*>(rec + i * REC_FLOATS + 4);    // con.z, opacity*coef, depth
@@ -352,92 +405,52 @@ gauss_bwd_kernel(int P, int D, int M, const float* __restrict__ means3D, const i
         o_rot[3] += 2 * r * (dRt[0][1] - dRt[1][0]) + 2 * x * (dRt[2][0] + dRt[0][2]) + 2 * y * (dRt[1][2] + dRt[2][1]) - 4 * z * (dRt[1][1] + dRt[0][0]);
       }
     }
-  }
 
-  // ---------------- write every output exactly once, coalesced ----------------
-  // Per-thread stores of 3/4/6/48-float rows are strided across the warp (20 sectors per request measured);
-  // stage the block's rows in shared memory and stream each output array out as contiguous 16-byte stores.
-  float* s_sh = s_tile;   // the generic (M != 16 / unaligned) path keeps 19 floats per Gaussian here instead
-  const bool use_tma = WRITE_SH && M == 16 && (reinterpret_cast<uintptr_t>(dL_dsh) & 15) == 0;
-  const int t = threadIdx.x;
-  float* sp = s_out;
-  // array order and widths: mean2D 3, conic 4, opacity 1, color 3, depth 1, mean3D 3, cov3D 6, norm3D 3, scale 3, rot 4
-  float* s_mean2D = sp; sp += GB_THREADS * 3;
-  float* s_conic = sp; sp += GB_THREADS * 4;
-  float* s_opac = sp; sp += GB_THREADS * 1;
-  float* s_color = sp; sp += GB_THREADS * 3;
-  float* s_depth = sp; sp += GB_THREADS * 1;
-  float* s_mean = sp; sp += GB_THREADS * 3;
-  float* s_cov = sp; sp += GB_THREADS * 6;
-  float* s_norm = sp; sp += GB_THREADS * 3;
-  float* s_scale = sp; sp += GB_THREADS * 3;
-  float* s_rot = sp;
-  s_mean2D[3 * t] = o_mean2D[0]; s_mean2D[3 * t + 1] = o_mean2D[1]; s_mean2D[3 * t + 2] = o_mean2D[2];
-  *reinterpret_cast<float4*>(s_conic + 4 * t) = make_float4(o_conic[0], o_conic[1], o_conic[2], o_conic[3]);
-  s_opac[t] = o_opac;
-  s_color[3 * t] = o_color[0]; s_color[3 * t + 1] = o_color[1]; s_color[3 * t + 2] = o_color[2];
-  s_depth[t] = o_depth;
-  s_mean[3 * t] = o_mean[0]; s_mean[3 * t + 1] = o_mean[1]; s_mean[3 * t + 2] = o_mean[2];
+    // ---------------- this Gaussian's rows ----------------
+    auto store3 = [&](float* dst, const float* v) { float* d = dst + 3 * i; d[0] = v[0]; d[1] = v[1]; d[2] = v[2]; };
+    auto store4 = [&](float* dst, float v0, float v1, float v2, float v3) {
+      float* d = dst + 4 * i;
+      if ((reinterpret_cast<uintptr_t>(d) & 15) == 0) *reinterpret_cast<float4*>(d) = make_float4(v0, v1, v2, v3);
+      else { d[0] = v0; d[1] = v1; d[2] = v2; d[3] = v3; }
+    };
+    store3(dL_dmean2D, o_mean2D);
+    store4(dL_dconic, o_conic[0], o_conic[1], o_conic[2], o_conic[3]);
+    dL_dopacity[i] = o_opac;
+    store3(dL_dcolor, o_color);
+    dL_ddepth[i] = o_depth;
+    store3(dL_dmean3D, o_mean);
+    {
+      float* d = dL_dcov3D + 6 * i;
+      if ((reinterpret_cast<uintptr_t>(d) & 7) == 0) {
+        reinterpret_cast<float2*>(d)[0] = make_float2(o_cov[0], o_cov[1]);
+        reinterpret_cast<float2*>(d)[1] = make_float2(o_cov[2], o_cov[3]);
+        reinterpret_cast<float2*>(d)[2] = make_float2(o_cov[4], o_cov[5]);
+      } else {
 #pragma unroll
-  for (int k = 0; k < 6; k++) s_cov[6 * t + k] = o_cov[k];
-  s_norm[3 * t] = o_norm[0]; s_norm[3 * t + 1] = o_norm[1]; s_norm[3 * t + 2] = o_norm[2];
-  s_scale[3 * t] = o_scale[0]; s_scale[3 * t + 1] = o_scale[1]; s_scale[3 * t + 2] = o_scale[2];
-  *reinterpret_cast<float4*>(s_rot + 4 * t) = make_float4(o_rot[0], o_rot[1], o_rot[2], o_rot[3]);
-  if (WRITE_SH && !use_tma) {
-    __syncthreads();   // s_tile may still hold other threads' staged SH coefficients
-#pragma unroll
-    for (int k = 0; k < 16; k++) s_sh[19 * t + k] = dsh_scale[k];
-    s_sh[19 * t + 16] = dL_dRGB[0]; s_sh[19 * t + 17] = dL_dRGB[1]; s_sh[19 * t + 18] = dL_dRGB[2];
-  }
-  __syncthreads();
-  const size_t base = (size_t)blockIdx.x * GB_THREADS;            // first Gaussian of this block
-  const int nvalid = min(GB_THREADS, P - (int)base);              // Gaussians of this block that exist
-  auto stream_out = [&](const float* src, float* dst, int width) {
-    const int nfl = nvalid * width;                                // floats to write, contiguous in dst
-    float* d = dst + base * width;                                 // 16-byte aligned: base is a multiple of 128
-    const int nv4 = ((reinterpret_cast<uintptr_t>(d) & 15) == 0) ? (nfl >> 2) : 0;   // caller buffers may be unaligned
-    for (int i = t; i < nv4; i += GB_THREADS) reinterpret_cast<float4*>(d)[i] = reinterpret_cast<const float4*>(src)[i];
-    for (int i = (nv4 << 2) + t; i < nfl; i += GB_THREADS) d[i] = src[i];
-  };
-  stream_out(s_mean2D, dL_dmean2D, 3);
-  stream_out(s_conic, dL_dconic, 4);
-  stream_out(s_opac, dL_dopacity, 1);
-  stream_out(s_color, dL_dcolor, 3);
-  stream_out(s_depth, dL_ddepth, 1);
-  stream_out(s_mean, dL_dmean3D, 3);
-  stream_out(s_cov, dL_dcov3D, 6);
-  stream_out(s_norm, dL_dnorm3D, 3);
-  stream_out(s_scale, dL_dscale, 3);
-  stream_out(s_rot, dL_drot, 4);
-  if (WRITE_SH) {
-    // dL_dsh[g][k][ch] = dRGB/dsh_k(g) * dL_dRGB[ch](g)
-    const int row = 3 * M;
-    const int nfl = nvalid * row;
-    float* d = dL_dsh + base * row;
-    if (use_tma) {
-      // The block's 128 x 192-byte rows are one contiguous 24 KB span of dL_dsh: build it in shared memory and
-      // hand it to the TMA engine as a single bulk store (cp.async.bulk, shared::cta -> global).
-      float* rowp = s_tile + 48 * t;
-#pragma unroll
-      for (int k4 = 0; k4 < 12; k4++) {
-        float v[4];
-#pragma unroll
-        for (int c = 0; c < 4; c++) { const int r = 4 * k4 + c; v[c] = dsh_scale[r / 3] * dL_dRGB[r % 3]; }
-        *reinterpret_cast<float4*>(rowp + 4 * k4) = make_float4(v[0], v[1], v[2], v[3]);
+        for (int q = 0; q < 6; q++) d[q] = o_cov[q];
       }
-      asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // generic-proxy writes -> visible to the async proxy
-      __syncthreads();
-      if (t == 0) {
-        const unsigned src = (unsigned)__cvta_generic_to_shared(s_tile);
-        const unsigned bytes = (unsigned)nfl * 4u;
-        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(d), "r"(src), "r"(bytes) : "memory");
-        asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
-        asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");   // shared memory must outlive the read
-      }
-    } else {
-      for (int i = t; i < nfl; i += GB_THREADS) {
-        const int gl = i / row, r = i - gl * row, k = r / 3, ch = r - 3 * k;
-        d[i] = (k < 16 ? s_sh[19 * gl + k] : 0.f) * s_sh[19 * gl + 16 + ch];
+    }
+    store3(dL_dnorm3D, o_norm);
+    store3(dL_dscale, o_scale);
+    store4(dL_drot, o_rot[0], o_rot[1], o_rot[2], o_rot[3]);
+    if (WRITE_SH) {
+      // dL_dsh[g][k][ch] = dRGB/dsh_k(g) * dL_dRGB[ch](g)
+      if (sh_fast) {
+        float4* d4 = reinterpret_cast<float4*>(dL_dsh + i * 48);
+#pragma unroll
+        for (int k4 = 0; k4 < 12; k4++) {
+          float v[4];
+#pragma unroll
+          for (int c = 0; c < 4; c++) { const int r = 4 * k4 + c; v[c] = dsh_scale[r / 3] * dL_dRGB[r % 3]; }
+          d4[k4] = make_float4(v[0], v[1], v[2], v[3]);
+        }
+      } else {
+        float* sc = s_tile + 19 * t;   // per-thread scratch: dynamic indexing without local memory
+#pragma unroll
+        for (int q = 0; q < 16; q++) sc[q] = dsh_scale[q];
+        sc[16] = dL_dRGB[0]; sc[17] = dL_dRGB[1]; sc[18] = dL_dRGB[2];
+        float* d = dL_dsh + i * 3 * M;
+        for (int r = 0; r < 3 * M; r++) { const int kk = r / 3, ch = r - 3 * kk; d[r] = (kk < 16 ? sc[kk] : 0.f) * sc[16 + ch]; }
       }
     }
   }
@@ -447,7 +460,7 @@ gauss_bwd_kernel(int P, int D, int M, const float* __restrict__ means3D, const i
 
 void sfgs_launch_gauss_bwd(const sfgs_backward_args* a, const GeomLayout& g, float focal_x, float focal_y,
                            const float* acc, cudaStream_t st) {
-  const int blocks = (a->P + GB_THREADS - 1) / GB_THREADS;
+  const int blocks = (a->P + GB_SPAN - 1) / GB_SPAN;
   const float* cov3D_ptr = a->cov3D_precomp != nullptr ? a->cov3D_precomp : g.cov3D;
   SFGS_COUNT_LAUNCH();
   if (a->M > 0 && a->dL_dsh != nullptr)

@@ -29,7 +29,7 @@ namespace {
 
 constexpr int BWD_THREADS = 256;
 constexpr int BWD_WARPS = BWD_THREADS / 32;
-constexpr int BWD_BATCH = 64;     // records staged per step
+constexpr int BWD_BATCH = 128;    // records staged per step
 constexpr int CH = 16;            // records per phase-2 chunk
 constexpr int PIXF = 12;          // floats per pixel-table row: dLc[3], dLd, dLn[3], px, py, pad[3]
 
