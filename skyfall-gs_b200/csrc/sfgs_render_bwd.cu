@@ -33,14 +33,16 @@ constexpr int BWD_BATCH = 128;    // records staged per step
 constexpr int CH = 16;            // records per phase-2 chunk
 constexpr int PIXF = 12;          // floats per pixel-table row: dLc[3], dLd, dLn[3], px, py, pad[3]
 
+constexpr int RING = 3;           // staged batches kept: the one being read, the one in flight, and the previous one
+
 struct BwdSmem {
-  float4 rec[2][BWD_BATCH][4];                 // 8 KB   staged blend records
-  uint32_t id[2][BWD_BATCH];
+  float4 rec[RING][BWD_BATCH][4];              // 24 KB  staged blend records
+  uint32_t id[RING][BWD_BATCH];
   uint32_t bits[2][BWD_WARPS][BWD_BATCH / 32]; // per block: which staged records can reach it
   uint32_t maxc[BWD_WARPS];
   float2 wh[BWD_WARPS][32][CH + 1];            // 34 KB  phase-1 -> phase-2 hand-over, [pixel][record], padded
   float pix[BWD_THREADS][PIXF];                // 12 KB  per-pixel cotangents and coordinates
-  float4 cparam[BWD_WARPS][CH][2];             // 4 KB   per chunk slot: (mx,my,con.x,con.y), (con.z,opac,id bits,-)
+  uint32_t cref[BWD_WARPS][CH];                // per chunk slot: ring position (stage * BATCH + e) of its record
 };
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
@@ -136,7 +138,7 @@ render_bwd_kernel(const uint2* __restrict__ ranges, const char* __restrict__ bin
   const int nbatches = (used + BWD_BATCH - 1) / BWD_BATCH;
 
   // batch b holds positions used-1-b*BATCH-e, e = 0..BATCH-1 (back to front); thread e stages record e
-  auto issue = [&](int batch, int stage) {
+  auto issue = [&](int batch, int stage, int bstage) {
     unsigned m = 0;
     if (tid < BWD_BATCH) {
       const int pos = used - 1 - batch * BWD_BATCH - tid;
@@ -156,7 +158,7 @@ render_bwd_kernel(const uint2* __restrict__ ranges, const char* __restrict__ bin
 #pragma unroll
       for (int blk = 0; blk < BWD_WARPS; blk++) {
         const unsigned word = __ballot_sync(0xffffffffu, (m >> blk) & 1u);
-        if (lane == 0) S.bits[stage][blk][wid] = word;
+        if (lane == 0) S.bits[bstage][blk][wid] = word;
       }
     }
   };
@@ -166,8 +168,11 @@ render_bwd_kernel(const uint2* __restrict__ ranges, const char* __restrict__ bin
   auto phase2 = [&](int n) {
     __syncwarp();
     const bool have = ck < n;
-    const float4 ra = S.cparam[wid][ck][0];   // mx, my, con.x, con.y
-    const float4 rb = S.cparam[wid][ck][1];   // con.z, opac, id bits
+    const uint32_t ref = have ? S.cref[wid][ck] : 0u;
+    const float4* rp = &S.rec[0][0][0] + ref * 4;
+    const float4 ra = rp[0];                  // mx, my, con.x, con.y
+    const float4 rb = rp[1];                  // con.z, opac, depth
+    const uint32_t gid = (&S.id[0][0])[ref];
     float s0 = 0, s1 = 0, s2 = 0, s3 = 0, s4 = 0, s5 = 0, s6 = 0;      // sum w * dL/dpix_c
     float sh = 0, shx = 0, shy = 0, shxx = 0, shxy = 0, shyy = 0, sab = 0;
     const int pbase = wid * 32 + chalf * 16;
@@ -192,7 +197,7 @@ render_bwd_kernel(const uint2* __restrict__ ranges, const char* __restrict__ bin
 #undef XH
     if (have) {
       const float o = rb.y;
-      float* dst = acc + (size_t)__float_as_uint(rb.z) * 16;
+      float* dst = acc + (size_t)gid * 16;
       if (chalf == 0) {
         red_add_v4(dst, make_float4(s0, s1, s2, s3));
         red_add_v4(dst + 4, make_float4(s4, s5, s6, -ddelx_dx * o * fmaf(ra.z, shx, ra.w * shy)));
@@ -205,21 +210,21 @@ render_bwd_kernel(const uint2* __restrict__ ranges, const char* __restrict__ bin
     __syncwarp();
   };
 
-  const unsigned cparam_addr = (unsigned)__cvta_generic_to_shared(&S.cparam[wid][0][0]) + (unsigned)(lane & 1) * 16u;
-  issue(0, 0);
-  int kcur = 0;   // fill level of this warp's chunk; persists across batches
+  issue(0, 0, 0);
+  int kcur = 0;     // fill level of this warp's chunk; a chunk may span two consecutive batches
+  int cbirth = 0;   // batch in which the chunk's first record was staged
   for (int b = 0; b < nbatches; b++) {
-    const int stage = b & 1;
+    const int stage = b % RING, bstage = b & 1;
     cp_async_wait_all();
-    __syncthreads();   // stage visible to all; the other stage is no longer read by anyone
-    if (b + 1 < nbatches) issue(b + 1, stage ^ 1);
+    __syncthreads();   // batch b visible to all; ring slot (b+1)%RING held batch b-2, which no chunk references any more
+    if (b + 1 < nbatches) issue(b + 1, (b + 1) % RING, bstage ^ 1);
     const int first_pos = used - 1 - b * BWD_BATCH;
 
     // records this warp can use: reach bit set and pos < wmax  <=>  e >= first_pos - wmax + 1
     int e0 = first_pos - (int)wmax + 1;
     if (e0 < 0) e0 = 0;
     for (int word = e0 >> 5; word < BWD_BATCH / 32; word++) {
-      unsigned bits = S.bits[stage][wid][word];
+      unsigned bits = S.bits[bstage][wid][word];
       if (word == (e0 >> 5)) bits &= 0xffffffffu << (e0 & 31);
       while (bits) {
         const int e = word * 32 + __ffs(bits) - 1;
@@ -238,7 +243,10 @@ render_bwd_kernel(const uint2* __restrict__ ranges, const char* __restrict__ bin
         if (active) {
           const float4 rc = S.rec[stage][e][2];   // r, g, b, nx
           const float4 rd = S.rec[stage][e][3];   // ny, nz
-          const float inv_1ma = __frcp_rn(1.f - alpha);   // shared by the T recovery and the background term
+          // 1 - alpha is in [0.01, 1]: the approximate reciprocal (1 ulp, one MUFU) needs no range fix-up; it is shared
+          // by the T recovery and the background term
+          float inv_1ma;
+          asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv_1ma) : "f"(1.f - alpha));
           T = T * inv_1ma;
           const float weight = alpha * T;
           // two independent chains: halves the dependent-FMA latency of the dot product
@@ -267,21 +275,14 @@ render_bwd_kernel(const uint2* __restrict__ ranges, const char* __restrict__ bin
           h_out = G * dL_dalpha;
         }
         S.wh[wid][lane][kcur] = make_float2(w_out, h_out);
-        {
-          // lanes 0 and 1 park the record's parameters with the chunk slot: select + one predicated store, no branch
-          const float idf = __uint_as_float(S.id[stage][e]);
-          asm volatile(
-              "{\n\t.reg .pred p0, p2;\n\t.reg .f32 a, b, c, d;\n\t"
-              "setp.eq.u32 p0, %0, 0;\n\tsetp.lt.u32 p2, %0, 2;\n\t"
-              "selp.f32 a, %2, %6, p0;\n\tselp.f32 b, %3, %7, p0;\n\tselp.f32 c, %4, %8, p0;\n\tselp.f32 d, %5, 0f00000000, p0;\n\t"
-              "@p2 st.shared.v4.f32 [%1], {a, b, c, d};\n\t}\n" ::"r"(lane),
-              "r"(cparam_addr + (unsigned)kcur * 32u), "f"(ra.x), "f"(ra.y), "f"(ra.z), "f"(ra.w), "f"(rb.x), "f"(rb.y),
-              "f"(idf)
-              : "memory");
-        }
+        // the record itself stays in the staging ring; the chunk slot only remembers where
+        if (lane == 0) S.cref[wid][kcur] = (uint32_t)(stage * BWD_BATCH + e);
+        if (kcur == 0) cbirth = b;
         if (++kcur == CH) { phase2(CH); kcur = 0; }
       }
     }
+    // a chunk started in the previous batch must go now: its ring slot is overwritten during the next batch
+    if (kcur && cbirth < b) { phase2(kcur); kcur = 0; }
   }
   if (kcur) phase2(kcur);
 }
