@@ -88,7 +88,7 @@ typedef struct sfgs_forward_args {
   /* outputs (every element is written; no pre-zeroing required) */
   float* out_color;   /* [3,H,W] */
   float* out_depth;   /* [1,H,W] */
-  float* out_norm;    /* [3,H,W] (un-normalised, as the reference) */
+  float* out_norm;    /* [3,H,W] (un-normalised, as the reference; unit length when out_norm_raw is given) */
   float* out_alpha;   /* [1,H,W] */
   float* out_extra;   /* [ED,H,W] or NULL */
   int*   radii;       /* [P] */
@@ -100,6 +100,10 @@ typedef struct sfgs_forward_args {
    * [tile_row_begin, tile_row_end) of the full tile grid are binned and blended, and only their pixels are
    * written.  radii still report visibility in the FULL image.  0,0 = the whole image. */
   int tile_row_begin, tile_row_end;
+  /* optional fused post-op (the reference normalises the blended normal map in torch,
+   * RAST/diff_gauss/__init__.py:48): when non-NULL, out_norm receives F.normalize(blend, p=2, dim=0, eps=1e-12)
+   * and the un-normalised blend is stored here ([3,H,W]) for the backward. */
+  float* out_norm_raw;
 } sfgs_forward_args;
 
 /* Returns num_rendered (>= 0) or a negative SFGS_E_* code. */
@@ -153,6 +157,9 @@ typedef struct sfgs_backward_args {
   void* stream;
   /* the same band the forward used (0,0 = whole image); gradients are then partial sums over the band */
   int tile_row_begin, tile_row_end;
+  /* optional: the forward's out_norm_raw.  When non-NULL, dL_dpix_norm is the gradient w.r.t. the UNIT normal
+   * map and the blend adjoint applies the adjoint of F.normalize while it loads the pixel. */
+  const float* norm_raw;
 } sfgs_backward_args;
 
 int sfgs_rasterize_backward(const sfgs_backward_args* a);

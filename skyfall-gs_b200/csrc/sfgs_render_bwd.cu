@@ -66,7 +66,7 @@ render_bwd_kernel(const uint2* __restrict__ ranges, const char* __restrict__ bin
                   const uint32_t* __restrict__ n_contrib, const float* __restrict__ dL_dpixels,
                   const float* __restrict__ dL_dpixel_depths, const float* __restrict__ dL_dpixel_norms,
                   const float* __restrict__ dL_dpixel_alphas, const float* __restrict__ dL_dpixel_extras,
-                  float* __restrict__ acc /* [P,16] zero-initialised */, float* __restrict__ dL_dextras) {
+                  const float* __restrict__ norm_raw, float* __restrict__ acc /* [P,16] zero-initialised */, float* __restrict__ dL_dextras) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   BwdSmem& S = *reinterpret_cast<BwdSmem*>(smem_raw);
 
@@ -101,6 +101,20 @@ render_bwd_kernel(const uint2* __restrict__ ranges, const char* __restrict__ bin
     dLd = dL_dpixel_depths[pix_id];
     dLn0 = dL_dpixel_norms[0 * HW + pix_id]; dLn1 = dL_dpixel_norms[1 * HW + pix_id]; dLn2 = dL_dpixel_norms[2 * HW + pix_id];
     dLa = dL_dpixel_alphas[pix_id];
+    if (norm_raw != nullptr) {
+      // dL_dpixel_norms is w.r.t. the unit normal y = x / max(|x|, eps): apply the adjoint of F.normalize here
+      // (torch: g/d - [|x| >= eps] (g.x)/d^2 * x/|x|, d = max(|x|, eps))
+      const float x0 = norm_raw[0 * HW + pix_id], x1 = norm_raw[1 * HW + pix_id], x2 = norm_raw[2 * HW + pix_id];
+      const float n = sqrtf(x0 * x0 + x1 * x1 + x2 * x2);
+      const float d = fmaxf(n, 1e-12f);
+      const float gx = dLn0 * x0 + dLn1 * x1 + dLn2 * x2;
+      float r0 = dLn0 / d, r1 = dLn1 / d, r2 = dLn2 / d;
+      if (n >= 1e-12f) {
+        const float s = gx / (d * d) / n;
+        r0 -= s * x0; r1 -= s * x1; r2 -= s * x2;
+      }
+      dLn0 = r0; dLn1 = r1; dLn2 = r2;
+    }
   }
   float bg_dot = 0;
   bg_dot += bg_color[0] * dLc0; bg_dot += bg_color[1] * dLc1; bg_dot += bg_color[2] * dLc2;
@@ -307,10 +321,10 @@ void sfgs_launch_render_bwd(const sfgs_backward_args* a, const GeomLayout& g, co
     render_bwd_kernel<true><<<grid, BWD_THREADS, smem, st>>>(
         im.ranges, (const char*)b.point_list, im.hdr, a->width, a->height, a->ED, band0, a->background, g.rec,
         a->extra_attrs, a->accum_alphas, im.n_contrib, a->dL_dpix, a->dL_dpix_depth, a->dL_dpix_norm,
-        a->dL_dpix_alpha, a->dL_dpix_extra, acc, a->dL_dextra);
+        a->dL_dpix_alpha, a->dL_dpix_extra, a->norm_raw, acc, a->dL_dextra);
   else
     render_bwd_kernel<false><<<grid, BWD_THREADS, smem, st>>>(
         im.ranges, (const char*)b.point_list, im.hdr, a->width, a->height, 0, band0, a->background, g.rec, nullptr,
-        a->accum_alphas, im.n_contrib, a->dL_dpix, a->dL_dpix_depth, a->dL_dpix_norm, a->dL_dpix_alpha, nullptr, acc,
-        nullptr);
+        a->accum_alphas, im.n_contrib, a->dL_dpix, a->dL_dpix_depth, a->dL_dpix_norm, a->dL_dpix_alpha, nullptr,
+        a->norm_raw, acc, nullptr);
 }

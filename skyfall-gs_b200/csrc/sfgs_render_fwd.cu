@@ -37,8 +37,8 @@ render_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
                   int band0,
                   const float* __restrict__ rec, const float* __restrict__ extras,
                   const float* __restrict__ bg_color, float* __restrict__ out_color,
-                  float* __restrict__ out_depth, float* __restrict__ out_norm, float* __restrict__ out_alpha,
-                  float* __restrict__ out_extra, uint32_t* __restrict__ n_contrib) {
+                  float* __restrict__ out_depth, float* __restrict__ out_norm, float* __restrict__ out_norm_raw,
+                  float* __restrict__ out_alpha, float* __restrict__ out_extra, uint32_t* __restrict__ n_contrib) {
   if (hdr[HDR_OVERFLOW]) return;
   __shared__ __align__(16) float4 s_rec[FWD_STAGES][FWD_BATCH][4];   // 32 KB
   __shared__ uint32_t s_id[FWD_STAGES][FWD_BATCH];
@@ -142,6 +142,15 @@ render_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
     out_color[1 * HW + pix_id] = C1 + T * bg_color[1];
     out_color[2 * HW + pix_id] = C2 + T * bg_color[2];
     out_depth[pix_id] = Dp;
+    if (out_norm_raw != nullptr) {
+      // fused post-op: F.normalize(norm, p=2, dim=0, eps=1e-12) (RAST/diff_gauss/__init__.py:48); the raw blend is
+      // kept for the adjoint
+      out_norm_raw[0 * HW + pix_id] = N0;
+      out_norm_raw[1 * HW + pix_id] = N1;
+      out_norm_raw[2 * HW + pix_id] = N2;
+      const float d = fmaxf(sqrtf(N0 * N0 + N1 * N1 + N2 * N2), 1e-12f);
+      N0 = N0 / d; N1 = N1 / d; N2 = N2 / d;
+    }
     out_norm[0 * HW + pix_id] = N0;
     out_norm[1 * HW + pix_id] = N1;
     out_norm[2 * HW + pix_id] = N2;
@@ -162,10 +171,11 @@ void sfgs_launch_render_fwd(const sfgs_forward_args* a, const GeomLayout& g, con
   if (a->ED > 0)
     render_fwd_kernel<true><<<grid, FWD_THREADS, 0, st>>>(im.ranges, b.point_list, b.inst_mask, im.hdr, a->width, a->height, a->ED, band0,
                                                          g.rec, a->extra_attrs, a->background, a->out_color,
-                                                         a->out_depth, a->out_norm, a->out_alpha, a->out_extra,
-                                                         im.n_contrib);
+                                                         a->out_depth, a->out_norm, a->out_norm_raw, a->out_alpha,
+                                                         a->out_extra, im.n_contrib);
   else
     render_fwd_kernel<false><<<grid, FWD_THREADS, 0, st>>>(im.ranges, b.point_list, b.inst_mask, im.hdr, a->width, a->height, 0, band0,
                                                           g.rec, nullptr, a->background, a->out_color, a->out_depth,
-                                                          a->out_norm, a->out_alpha, nullptr, im.n_contrib);
+                                                          a->out_norm, a->out_norm_raw, a->out_alpha, nullptr,
+                                                          im.n_contrib);
 }

@@ -29,6 +29,12 @@ from . import _C  # noqa: E402
 
 MAX_EXTRA_DIMS = 34  # RAST/cuda_rasterizer/auxiliary.h:20
 
+# The reference normalises the blended normal map with torch ops inside the autograd graph
+# (RAST/diff_gauss/__init__.py:48: ~4 elementwise kernels forward, ~8 backward, three passes over 3·H·W floats).
+# Here the blend kernel writes the unit normals itself and the blend adjoint applies the normalize adjoint while
+# it loads each pixel's cotangent.  Set SFGS_FUSE_NORMALIZE=0 to get the torch post-op back.
+FUSE_NORMALIZE = os.environ.get("SFGS_FUSE_NORMALIZE", "1") != "0"
+
 
 class GaussianRasterizationSettings(NamedTuple):
     image_height: int
@@ -68,7 +74,7 @@ def _guarded(fn, args, debug, dump_name, label):
 class _RasterizeGaussians(torch.autograd.Function):
     @staticmethod
     def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
-                norm3Ds_precomp, extra_attrs, raster_settings):
+                norm3Ds_precomp, extra_attrs, raster_settings, fuse_normalize=False):
         rs = raster_settings
         n_extra = extra_attrs.shape[1] if extra_attrs.shape[0] != 0 else 0
         assert n_extra <= MAX_EXTRA_DIMS
@@ -76,13 +82,19 @@ class _RasterizeGaussians(torch.autograd.Function):
                        cov3Ds_precomp, norm3Ds_precomp, extra_attrs, n_extra, rs.viewmatrix, rs.projmatrix,
                        rs.tanfovx, rs.tanfovy, rs.kernel_size, rs.image_height, rs.image_width, sh, rs.sh_degree,
                        rs.campos, rs.prefiltered, rs.debug)
-        (num_rendered, color, depth, norm, alpha, radii, extra,
-         geom_buf, binning_buf, img_buf) = _guarded(_C.rasterize_gaussians, native_args, rs.debug,
-                                                    "snapshot_fw.dump", "forward")
+        ctx.fused = bool(fuse_normalize)
+        if ctx.fused:
+            (num_rendered, color, depth, norm, alpha, radii, extra, geom_buf, binning_buf, img_buf,
+             norm_raw) = _guarded(_C.rasterize_gaussians_fused, native_args, rs.debug, "snapshot_fw.dump", "forward")
+        else:
+            (num_rendered, color, depth, norm, alpha, radii, extra,
+             geom_buf, binning_buf, img_buf) = _guarded(_C.rasterize_gaussians, native_args, rs.debug,
+                                                        "snapshot_fw.dump", "forward")
+            norm_raw = torch.empty(0, device=means3D.device)
         ctx.raster_settings = rs
         ctx.num_rendered = num_rendered
         ctx.save_for_backward(colors_precomp, means3D, scales, rotations, cov3Ds_precomp, norm3Ds_precomp, radii,
-                              extra_attrs, sh, geom_buf, binning_buf, img_buf, alpha)
+                              extra_attrs, sh, geom_buf, binning_buf, img_buf, alpha, norm_raw)
         ctx.mark_non_differentiable(radii)
         return color, depth, norm, alpha, radii, extra
 
@@ -90,26 +102,29 @@ class _RasterizeGaussians(torch.autograd.Function):
     def backward(ctx, g_color, g_depth, g_norm, g_alpha, _g_radii, g_extra):
         rs = ctx.raster_settings
         (colors_precomp, means3D, scales, rotations, cov3Ds_precomp, norm3Ds_precomp, radii, extra_attrs, sh,
-         geom_buf, binning_buf, img_buf, alpha) = ctx.saved_tensors
+         geom_buf, binning_buf, img_buf, alpha, norm_raw) = ctx.saved_tensors
         native_args = (rs.bg, means3D, radii, colors_precomp, scales, rotations, extra_attrs, rs.scale_modifier,
                        cov3Ds_precomp, norm3Ds_precomp, rs.viewmatrix, rs.projmatrix, rs.tanfovx, rs.tanfovy,
                        rs.kernel_size, g_color, g_depth, g_norm, g_alpha, g_extra, sh, rs.sh_degree, rs.campos,
                        geom_buf, ctx.num_rendered, binning_buf, img_buf, alpha, rs.debug)
+        bwd = _C.rasterize_gaussians_backward
+        if ctx.fused:
+            bwd = lambda *a: _C.rasterize_gaussians_backward_fused(*a, norm_raw=norm_raw)  # noqa: E731
         (g_means2D, g_colors, g_opac, g_means3D, g_cov3D, g_norm3D, g_sh, g_scales, g_rot,
-         g_extra_attrs) = _guarded(_C.rasterize_gaussians_backward, native_args, rs.debug,
-                                   "snapshot_bw.dump", "backward")
-        # order of forward's inputs; the settings tuple gets no gradient
+         g_extra_attrs) = _guarded(bwd, native_args, rs.debug, "snapshot_bw.dump", "backward")
+        # order of forward's inputs; the settings tuple and the fusion flag get no gradient
         return (g_means3D, g_means2D, g_sh, g_colors, g_opac, g_scales, g_rot, g_cov3D, g_norm3D, g_extra_attrs,
-                None)
+                None, None)
 
 
 def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
                         norm3Ds_precomp, extra_attrs, raster_settings):
     color, depth, norm, alpha, radii, extra = _RasterizeGaussians.apply(
         means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, norm3Ds_precomp,
-        extra_attrs, raster_settings)
-    # the reference normalises the blended normal map in torch, inside the autograd graph (diff_gauss/__init__.py:48)
-    norm = torch.nn.functional.normalize(norm, p=2, dim=0)
+        extra_attrs, raster_settings, FUSE_NORMALIZE)
+    if not FUSE_NORMALIZE:
+        # the reference normalises the blended normal map in torch, inside the autograd graph (diff_gauss/__init__.py:48)
+        norm = torch.nn.functional.normalize(norm, p=2, dim=0)
     return color, depth, norm, alpha, radii, extra
 
 

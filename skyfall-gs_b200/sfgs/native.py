@@ -37,6 +37,7 @@ class ForwardArgs(C.Structure):
         ("out_alpha", c_float_p), ("out_extra", c_float_p), ("radii", c_int_p),
         ("debug", C.c_int), ("stream", C.c_void_p), ("capacity_hint", C.c_longlong),
         ("tile_row_begin", C.c_int), ("tile_row_end", C.c_int),
+        ("out_norm_raw", c_float_p),
     ]
 
 
@@ -62,6 +63,7 @@ class BackwardArgs(C.Structure):
         ("scratch_alloc", ALLOC_FN), ("scratch_user", C.c_void_p),
         ("debug", C.c_int), ("stream", C.c_void_p),
         ("tile_row_begin", C.c_int), ("tile_row_end", C.c_int),
+        ("norm_raw", c_float_p),
     ]
 
 

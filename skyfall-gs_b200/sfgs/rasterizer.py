@@ -55,7 +55,10 @@ class _Arena:
 def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations, scale_modifier,
                         cov3Ds_precomp, norm3Ds_precomp, extra_attrs, attr_degree, viewmatrix, projmatrix,
                         tan_fovx, tan_fovy, kernel_size, image_height, image_width, sh, degree, campos,
-                        prefiltered, debug, capacity_hint=0, tile_rows=None):
+                        prefiltered, debug, capacity_hint=0, tile_rows=None, fuse_normalize=False):
+    """Same positional signature and return tuple as the reference's `_C.rasterize_gaussians`.  With
+    `fuse_normalize=True` the returned normal map is already F.normalize(., dim=0) (the reference's torch post-op,
+    diff_gauss/__init__.py:48) and the un-normalised blend is appended to the tuple for the backward."""
     if means3D.ndim != 2 or means3D.shape[1] != 3:
         raise RuntimeError("means3D must have dimensions (num_points, 3)")
     L = N.lib()
@@ -68,14 +71,16 @@ def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations,
         # the reference short-circuits: zero images, empty scratch (rasterize_points.cu:94)
         out_extra = torch.zeros((F, H, W), **fopt) if F > 0 else torch.empty(0, **fopt)
         empty = torch.empty(0, dtype=torch.uint8, device=dev)
-        return (0, torch.zeros((NUM_CHANNELS, H, W), **fopt), torch.zeros((1, H, W), **fopt),
-                torch.zeros((3, H, W), **fopt), torch.zeros((1, H, W), **fopt),
-                torch.zeros((P,), dtype=torch.int32, device=dev), out_extra, empty, empty.clone(), empty.clone())
+        ret = (0, torch.zeros((NUM_CHANNELS, H, W), **fopt), torch.zeros((1, H, W), **fopt),
+               torch.zeros((3, H, W), **fopt), torch.zeros((1, H, W), **fopt),
+               torch.zeros((P,), dtype=torch.int32, device=dev), out_extra, empty, empty.clone(), empty.clone())
+        return ret + (torch.zeros((3, H, W), **fopt),) if fuse_normalize else ret
 
     with torch.cuda.device(dev):
         # one allocation for the 8 image planes: colour(3) depth(1) alpha(1) normal(3)
-        planes = torch.empty((8, H, W), **fopt)
+        planes = torch.empty((11 if fuse_normalize else 8, H, W), **fopt)
         out_color, out_depth, out_alpha, out_norm = planes[0:3], planes[3:4], planes[4:5], planes[5:8]
+        norm_raw = planes[8:11] if fuse_normalize else None
         radii = torch.empty((P,), dtype=torch.int32, device=dev)
         out_extra = torch.empty((F, H, W), **fopt) if F > 0 else torch.empty(0, **fopt)
 
@@ -105,6 +110,7 @@ def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations,
         a.out_color, a.out_depth = out_color.data_ptr(), out_depth.data_ptr()
         a.out_norm, a.out_alpha = out_norm.data_ptr(), out_alpha.data_ptr()
         a.out_extra = out_extra.data_ptr() if F > 0 else None
+        a.out_norm_raw = norm_raw.data_ptr() if fuse_normalize else None
         a.radii = radii.data_ptr()
         a.debug = int(bool(debug))
         a.stream = torch.cuda.current_stream(dev).cuda_stream
@@ -112,15 +118,19 @@ def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations,
         if tile_rows is not None:
             a.tile_row_begin, a.tile_row_end = int(tile_rows[0]), int(tile_rows[1])
         rendered = N.check(L.sfgs_rasterize_forward(C.byref(a)), "sfgs_rasterize_forward")
-    return (rendered, out_color, out_depth, out_norm, out_alpha, radii, out_extra,
-            geom.tensor, binning.tensor, img.tensor)
+    ret = (rendered, out_color, out_depth, out_norm, out_alpha, radii, out_extra,
+           geom.tensor, binning.tensor, img.tensor)
+    return ret + (norm_raw,) if fuse_normalize else ret
 
 
 def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rotations, extra_attrs, scale_modifier,
                                  cov3Ds_precomp, norm3Ds_precomp, viewmatrix, projmatrix, tan_fovx, tan_fovy,
                                  kernel_size, dL_dout_color, dL_dout_depth, dL_dout_norm, dL_dout_alpha,
                                  dL_dout_extra, sh, degree, campos, geomBuffer, R, binningBuffer, imageBuffer,
-                                 out_alpha, debug, tile_rows=None):
+                                 out_alpha, debug, tile_rows=None, norm_raw=None):
+    """Same positional signature and return tuple as the reference's `_C.rasterize_gaussians_backward`.  With
+    `norm_raw` (the extra tensor a `fuse_normalize=True` forward returned) `dL_dout_norm` is taken w.r.t. the unit
+    normal map and the adjoint of F.normalize is applied inside the blend-adjoint kernel."""
     L = N.lib()
     P = int(means3D.shape[0])
     H, W = int(dL_dout_color.shape[1]), int(dL_dout_color.shape[2])
@@ -173,6 +183,7 @@ def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rot
         a.dL_dpix_depth = _ptr(dL_dout_depth, keep)
         a.dL_dpix_norm = _ptr(dL_dout_norm, keep)
         a.dL_dpix_alpha = _ptr(dL_dout_alpha, keep)
+        a.norm_raw = _ptr(norm_raw, keep) if norm_raw is not None else None
         a.dL_dpix_extra = _ptr(dL_dout_extra, keep) if F > 0 else None
         a.dL_dmean2D = outs["means2D"].data_ptr()
         a.dL_dconic = outs["conic"].data_ptr()

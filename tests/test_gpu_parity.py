@@ -279,6 +279,42 @@ def test_autograd_api_matches_native_calls(cuda_device):
     assert vis.dtype == torch.bool and int(vis.sum()) >= int((radii > 0).sum())
 
 
+def test_fused_normalize_matches_torch_post_op(cuda_device, monkeypatch):
+    """the F.normalize post-op of diff_gauss/__init__.py:48 fused into the blend kernels gives the
+    unit normal map and the gradients of the torch formulation (fp32 rounding apart)."""
+    import diff_gauss
+    from diff_gauss import GaussianRasterizationSettings, GaussianRasterizer
+    dev = cuda_device
+    scene, cam = S.blob_scene(3000, seed=77), S.simple_camera(200, 120)
+    d = Hh.to_torch(scene, cam, dev)
+    bg = torch.tensor([0.1, 0.0, 0.3], device=dev)
+    cot = [torch.from_numpy(c).to(dev) for c in S.cotangents(cam.width, cam.height, seed=9)]
+    results = {}
+    for fused in (True, False):
+        monkeypatch.setattr(diff_gauss, "FUSE_NORMALIZE", fused)
+        leaves = {k: d[k].clone().requires_grad_(True) for k in ("means3D", "opacities", "shs", "scales", "rotations")}
+        m2d = torch.zeros((scene.P, 3), device=dev, requires_grad=True)
+        rs = GaussianRasterizationSettings(cam.height, cam.width, cam.tanfovx, cam.tanfovy, 0.1,
+                                           torch.zeros(1, device=dev), bg, 1.0, d["viewmatrix"], d["projmatrix"], 3,
+                                           d["campos"], False, False)
+        color, depth, norm, alpha, radii, _ = GaussianRasterizer(rs)(
+            leaves["means3D"], m2d, leaves["opacities"], shs=leaves["shs"], scales=leaves["scales"],
+            rotations=leaves["rotations"])
+        # only pixels some Gaussian reached: elsewhere the raw normal is exactly 0 and the adjoint multiplies by 1/eps
+        w = (alpha.detach() > 0.02).float()
+        ((norm * cot[2] * w).sum() + 0.1 * (color * cot[0]).sum() + 0.1 * (depth * cot[1]).sum()).backward()
+        results[fused] = (norm.detach(), {k: v.grad.clone() for k, v in leaves.items()}, m2d.grad.clone())
+    n_f, g_f, m_f = results[True]
+    n_t, g_t, m_t = results[False]
+    assert (n_f - n_t).abs().max().item() <= 2e-6
+    covered = n_t.norm(dim=0) > 0.5
+    assert bool(covered.any()) and bool(((n_f.norm(dim=0) - 1).abs() < 1e-5)[covered].all())
+    for k in g_t:
+        tol = 1e-5 + 2e-4 * g_t[k].abs().max().item()
+        assert (g_f[k] - g_t[k]).abs().max().item() <= tol, k
+    assert (m_f - m_t).abs().max().item() <= 1e-5 + 2e-4 * m_t.abs().max().item()
+
+
 def test_mark_visible_matches_oracle(cuda_device):
     from oracle import cpu_oracle as O
     from sfgs import rasterizer as R
