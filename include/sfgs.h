@@ -193,6 +193,21 @@ int sfgs_binning_layout(char* base, long long capacity, sfgs_binning_view* out);
 /* capacity (in tile instances) the last forward on this buffer was sized for; stored in the image buffer header */
 long long sfgs_last_capacity(void);
 
+/* ---- fused per-Gaussian activations ------------------
+ * The torch pre-ops of every render() call as one kernel each way:
+ *   scales    = sqrt(exp(scaling_raw)^2 + filter_3D^2)          get_scaling_with_3D_filter, scene/gaussian_model.py:207-213
+ *   opacity   = sigmoid(opacity_raw) * sqrt(prod exp(s)^2 / prod(exp(s)^2 + f^2))   get_opacity_with_3D_filter, :237-249
+ *   rotations = rotation_raw / max(|rotation_raw|, 1e-12)       get_rotation, :215-217
+ * filter_3D is float64 [P] like the reference's (compute_3D_filter, :254-308); the mixed float32/float64
+ * promotion of the torch expressions is reproduced and the results are float32 (the `.float()` of
+ * gaussian_renderer/__init__.py:137-138).  rotation pointers must be 16-byte aligned. */
+int sfgs_activations_forward(int P, const float* opacity_raw, const float* scaling_raw, const float* rotation_raw,
+                             const double* filter_3D, float* opacity, float* scales, float* rotations, void* stream);
+int sfgs_activations_backward(int P, const float* opacity_raw, const float* scaling_raw, const float* rotation_raw,
+                              const double* filter_3D, const float* g_opacity, const float* g_scales,
+                              const float* g_rotations, float* g_opacity_raw, float* g_scaling_raw,
+                              float* g_rotation_raw, void* stream);
+
 /* ---- fused SSIM ---------------------------------------------------------- */
 int sfgs_fusedssim_forward(float C1, float C2, int B, int CH, int H, int W,
                            const float* img1, const float* img2, int train,

@@ -33,6 +33,13 @@ void sfgs_launch_render_fwd(const sfgs_forward_args* a, const GeomLayout& g, con
                             const BinningLayout& b, cudaStream_t st);
 void sfgs_launch_render_bwd(const sfgs_backward_args* a, const GeomLayout& g, const ImageLayout& im,
                             const BinningLayout& b, float* acc, cudaStream_t st);
+int sfgs_launch_activations_fwd(int P, const float* opacity_raw, const float* scaling_raw, const float* rotation_raw,
+                                const double* filter_3D, float* opacity, float* scales, float* rotations,
+                                cudaStream_t st);
+int sfgs_launch_activations_bwd(int P, const float* opacity_raw, const float* scaling_raw, const float* rotation_raw,
+                                const double* filter_3D, const float* g_opacity, const float* g_scales,
+                                const float* g_rotations, float* g_opacity_raw, float* g_scaling_raw,
+                                float* g_rotation_raw, cudaStream_t st);
 void sfgs_launch_gauss_bwd(const sfgs_backward_args* a, const GeomLayout& g, float focal_x, float focal_y,
                            const float* acc, cudaStream_t st);
 
@@ -301,6 +308,37 @@ int sfgs_rasterize_backward(const sfgs_backward_args* a) {
   sfgs_launch_gauss_bwd(a, g, focal_x, focal_y, acc, st);
   PROF_END();
   STAGE_CHECK("gauss_bwd");
+  return SFGS_OK;
+}
+
+int sfgs_activations_forward(int P, const float* opacity_raw, const float* scaling_raw, const float* rotation_raw,
+                             const double* filter_3D, float* opacity, float* scales, float* rotations, void* stream) {
+  if (P < 0) return fail(SFGS_E_BADARG, "activations_forward: P < 0");
+  if (P == 0) return SFGS_OK;
+  if (!opacity_raw || !scaling_raw || !rotation_raw || !filter_3D || !opacity || !scales || !rotations)
+    return fail(SFGS_E_BADARG, "activations_forward: null pointer");
+  if (sfgs_launch_activations_fwd(P, opacity_raw, scaling_raw, rotation_raw, filter_3D, opacity, scales, rotations,
+                                  (cudaStream_t)stream))
+    return fail(SFGS_E_BADARG, "activations_forward: rotation buffers must be 16-byte aligned");
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(SFGS_E_CUDA, "activations_forward", e);
+  return SFGS_OK;
+}
+
+int sfgs_activations_backward(int P, const float* opacity_raw, const float* scaling_raw, const float* rotation_raw,
+                              const double* filter_3D, const float* g_opacity, const float* g_scales,
+                              const float* g_rotations, float* g_opacity_raw, float* g_scaling_raw,
+                              float* g_rotation_raw, void* stream) {
+  if (P < 0) return fail(SFGS_E_BADARG, "activations_backward: P < 0");
+  if (P == 0) return SFGS_OK;
+  if (!opacity_raw || !scaling_raw || !rotation_raw || !filter_3D || !g_opacity || !g_scales || !g_rotations ||
+      !g_opacity_raw || !g_scaling_raw || !g_rotation_raw)
+    return fail(SFGS_E_BADARG, "activations_backward: null pointer");
+  if (sfgs_launch_activations_bwd(P, opacity_raw, scaling_raw, rotation_raw, filter_3D, g_opacity, g_scales, g_rotations,
+                                  g_opacity_raw, g_scaling_raw, g_rotation_raw, (cudaStream_t)stream))
+    return fail(SFGS_E_BADARG, "activations_backward: rotation buffers must be 16-byte aligned");
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(SFGS_E_CUDA, "activations_backward", e);
   return SFGS_OK;
 }
 

@@ -85,6 +85,7 @@ EXPORTS = [
     "sfgs_geom_bytes", "sfgs_image_bytes", "sfgs_binning_bytes",
     "sfgs_geom_layout", "sfgs_image_layout", "sfgs_binning_layout", "sfgs_last_capacity",
     "sfgs_fusedssim_forward", "sfgs_fusedssim_backward", "sfgs_dist2_knn3",
+    "sfgs_activations_forward", "sfgs_activations_backward",
     "sfgs_last_error", "sfgs_version", "sfgs_launch_count", "sfgs_profile_enable", "sfgs_profile_read", "sfgs_sizeof", "sfgs_sm_clock_probe",
 ]
 STAGE_NAMES = ["fwd_zero", "preprocess", "tile_scan", "emit_keys", "tile_sort", "render_fwd", "bwd_zero", "render_bwd",
@@ -124,6 +125,10 @@ def lib() -> C.CDLL:
     L.sfgs_fusedssim_backward.restype = C.c_int
     L.sfgs_dist2_knn3.argtypes = [C.c_int, C.c_void_p, C.c_void_p, ALLOC_FN, C.c_void_p, C.c_void_p]
     L.sfgs_dist2_knn3.restype = C.c_int
+    L.sfgs_activations_forward.argtypes = [C.c_int] + [C.c_void_p] * 8
+    L.sfgs_activations_forward.restype = C.c_int
+    L.sfgs_activations_backward.argtypes = [C.c_int] + [C.c_void_p] * 11
+    L.sfgs_activations_backward.restype = C.c_int
     L.sfgs_last_error.argtypes = []; L.sfgs_last_error.restype = C.c_char_p
     L.sfgs_version.argtypes = []; L.sfgs_version.restype = C.c_int
     L.sfgs_launch_count.argtypes = []; L.sfgs_launch_count.restype = C.c_longlong

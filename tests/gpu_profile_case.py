@@ -15,6 +15,8 @@ ap.add_argument("--impl", default="ours", choices=["ours", "ref"])
 ap.add_argument("--P", type=int, default=1_000_000)
 ap.add_argument("--iters", type=int, default=3)
 ap.add_argument("--cam", default="jax", choices=["jax", "orbit"])
+ap.add_argument("--time", action="store_true", help="print CUDA-event ms per fwd+bwd iteration (median)")
+ap.add_argument("--stages", action="store_true", help="ours only: print the median per-stage CUDA-event times")
 a = ap.parse_args()
 dev = torch.device("cuda:0")
 scene = S.city_scene(a.P, seed=0)
@@ -22,12 +24,33 @@ cam = S.jax004_camera() if a.cam == "jax" else S.orbit_camera()
 d = Hh.to_torch(scene, cam, dev)
 bg = torch.zeros(3, device=dev)
 cot = [torch.from_numpy(c).to(dev) for c in S.cotangents(cam.width, cam.height)]
+times = []
+stage_hist = {}
+if a.stages and a.impl == "ours":
+    from sfgs import native
 for it in range(a.iters):
+    if a.stages and a.impl == "ours":
+        native.profile_enable(True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
     if a.impl == "ours":
         f = Hh.run_ours_forward(d, cam, 3, bg)
         b = Hh.run_ours_backward(d, cam, 3, bg, f, cot)
     else:
         f = Hh.run_ref_forward(d, cam, 3, bg)
         b = Hh.run_ref_backward(d, cam, 3, bg, f, cot)
+    e1.record()
     torch.cuda.synchronize()
+    times.append(e0.elapsed_time(e1))
+    if a.stages and a.impl == "ours":
+        for k, v in native.profile_read().items():
+            stage_hist.setdefault(k, []).append(v[0] / v[1] if v[1] else 0.0)
 print("done", f["num_rendered"])
+if a.time:
+    srt = sorted(times[1:] or times)
+    V = int((f["radii"] > 0).sum())
+    print(f"impl={a.impl} cam={a.cam} P={a.P} V={V} R={int(f['num_rendered'])} median_ms={srt[len(srt) // 2]:.3f} min_ms={srt[0]:.3f} "
+          f"Mpix/s={cam.width * cam.height / srt[len(srt) // 2] / 1e3:.1f}")
+if stage_hist:
+    import statistics
+    print("stages_ms " + " ".join(f"{k}={statistics.median(v[1:] or v):.4f}" for k, v in stage_hist.items()))
