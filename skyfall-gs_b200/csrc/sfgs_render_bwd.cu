@@ -182,7 +182,7 @@ render_bwd_kernel(const uint2* __restrict__ ranges, const char* __restrict__ bin
   auto phase2 = [&](int n) {
     __syncwarp();
     const bool have = ck < n;
-    const uint32_t ref = have ? S.cref[wid][ck] : 0u;
+    const uint32_t ref = S.cref[wid][have ? ck : 0];   // idle lanes shadow slot 0 of the chunk (always valid, n >= 1)
     const float4* rp = &S.rec[0][0][0] + ref * 4;
     const float4 ra = rp[0];                  // mx, my, con.x, con.y
     const float4 rb = rp[1];                  // con.z, opac, depth
