@@ -218,8 +218,7 @@ int sfgs_rasterize_forward(const sfgs_forward_args* a) {
 
     // tile histogram + header start at zero
     PROF_BEGIN(ST_FWD_ZERO);
-    CU(cudaMemsetAsync(im.hdr, 0, IMG_HDR_WORDS * sizeof(uint32_t), st));
-    CU(cudaMemsetAsync(im.tile_count, 0, (size_t)im.tiles * sizeof(uint32_t), st));
+    CU(cudaMemsetAsync(im.hdr, 0, im.zero_bytes, st));   // header + tile histogram are adjacent
     PROF_END();
 
     if (P > 0) {

@@ -20,7 +20,7 @@ constexpr int SCAN_THREADS = 1024;
 constexpr int SCAN_ITEMS = 8;
 __global__ void __launch_bounds__(SCAN_THREADS)
 tile_scan_kernel(int tiles, const uint32_t* __restrict__ tile_count, uint2* __restrict__ ranges,
-                 uint32_t* __restrict__ tile_cursor, uint32_t* __restrict__ hdr, unsigned long long capacity) {
+                 uint32_t* __restrict__ hdr, unsigned long long capacity) {
   __shared__ uint32_t warp_sums[32];
   __shared__ uint32_t carry_s;
   __shared__ uint32_t maxlen_s;
@@ -32,9 +32,16 @@ tile_scan_kernel(int tiles, const uint32_t* __restrict__ tile_count, uint2* __re
     const int i0 = base + tid * SCAN_ITEMS;
     uint32_t v[SCAN_ITEMS];
     uint32_t x = 0;
+    const bool full = i0 + SCAN_ITEMS <= tiles;   // whole 8-item group in range: two 16-byte loads, four 16-byte stores
+    if (full) {
+      const uint4 a = reinterpret_cast<const uint4*>(tile_count + i0)[0], b = reinterpret_cast<const uint4*>(tile_count + i0)[1];
+      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else {
+#pragma unroll
+      for (int k = 0; k < SCAN_ITEMS; k++) v[k] = (i0 + k < tiles) ? tile_count[i0 + k] : 0u;
+    }
 #pragma unroll
     for (int k = 0; k < SCAN_ITEMS; k++) {
-      v[k] = (i0 + k < tiles) ? tile_count[i0 + k] : 0u;
       local_max = max(local_max, v[k]);
       x += v[k];
     }
@@ -53,14 +60,21 @@ tile_scan_kernel(int tiles, const uint32_t* __restrict__ tile_count, uint2* __re
     const uint32_t carry = carry_s;
     const uint32_t incl = carry + x + (wid > 0 ? warp_sums[wid - 1] : 0u);
     uint32_t run = incl - mine;   // exclusive prefix of this thread's first tile
+    // empty tiles read (0,0) exactly like the reference's memset + identifyTileRanges
+    uint2 rg[SCAN_ITEMS];
 #pragma unroll
     for (int k = 0; k < SCAN_ITEMS; k++) {
-      if (i0 + k < tiles) {
-        // empty tiles read (0,0) exactly like the reference's memset + identifyTileRanges
-        ranges[i0 + k] = v[k] ? make_uint2(run, run + v[k]) : make_uint2(0u, 0u);
-        tile_cursor[i0 + k] = 0u;
-      }
+      rg[k] = v[k] ? make_uint2(run, run + v[k]) : make_uint2(0u, 0u);
       run += v[k];
+    }
+    if (full) {
+#pragma unroll
+      for (int k = 0; k < SCAN_ITEMS; k += 2)
+        reinterpret_cast<uint4*>(ranges + i0)[k >> 1] = make_uint4(rg[k].x, rg[k].y, rg[k + 1].x, rg[k + 1].y);
+    } else {
+#pragma unroll
+      for (int k = 0; k < SCAN_ITEMS; k++)
+        if (i0 + k < tiles) ranges[i0 + k] = rg[k];
     }
     __syncthreads();
     if (tid == SCAN_THREADS - 1) carry_s = incl;
@@ -82,14 +96,24 @@ tile_scan_kernel(int tiles, const uint32_t* __restrict__ tile_count, uint2* __re
 
 // ---- key scatter ---------------------------------------------------------------
 // One thread per unsorted instance {gaussian, depth bits, tile, slot-in-tile}: no atomics, perfectly balanced.
+constexpr int SCATTER_ITEMS = 4;   // independent loads in flight per thread (the kernel is latency-bound)
 __global__ void __launch_bounds__(256)
 scatter_keys_kernel(const uint4* __restrict__ tmp, const uint2* __restrict__ ranges, const uint32_t* __restrict__ hdr,
                     uint64_t* __restrict__ keys) {
   if (hdr[HDR_OVERFLOW]) return;
-  const uint32_t i = blockIdx.x * 256u + threadIdx.x;
-  if (i >= hdr[HDR_R]) return;
-  const uint4 t = tmp[i];
-  keys[ranges[t.z].x + t.w] = ((uint64_t)t.y << 32) | t.x;
+  const uint32_t R = hdr[HDR_R];
+  const uint32_t i0 = blockIdx.x * (256u * SCATTER_ITEMS) + threadIdx.x;
+  uint4 t[SCATTER_ITEMS];
+  uint32_t start[SCATTER_ITEMS];
+#pragma unroll
+  for (int u = 0; u < SCATTER_ITEMS; u++)
+    if (i0 + 256u * u < R) t[u] = tmp[i0 + 256u * u];
+#pragma unroll
+  for (int u = 0; u < SCATTER_ITEMS; u++)
+    if (i0 + 256u * u < R) start[u] = ranges[t[u].z].x;
+#pragma unroll
+  for (int u = 0; u < SCATTER_ITEMS; u++)
+    if (i0 + 256u * u < R) keys[start[u] + t[u].w] = ((uint64_t)t[u].y << 32) | t[u].x;
 }
 
 // ---- per-tile sort -------------------------------------------------------------
@@ -227,12 +251,12 @@ tile_sort_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
 
 void sfgs_launch_tile_scan(const ImageLayout& im, unsigned long long capacity, cudaStream_t st) {
   SFGS_COUNT_LAUNCH();
-  tile_scan_kernel<<<1, SCAN_THREADS, 0, st>>>(im.tiles, im.tile_count, im.ranges, im.tile_cursor, im.hdr, capacity);
+  tile_scan_kernel<<<1, SCAN_THREADS, 0, st>>>(im.tiles, im.tile_count, im.ranges, im.hdr, capacity);
 }
 
 void sfgs_launch_scatter(const ImageLayout& im, const BinningLayout& b, unsigned long long capacity, cudaStream_t st) {
   SFGS_COUNT_LAUNCH();
-  const unsigned blocks = (unsigned)((capacity + 255) / 256);
+  const unsigned blocks = (unsigned)((capacity + 256 * SCATTER_ITEMS - 1) / (256 * SCATTER_ITEMS));
   if (blocks == 0) return;
   scatter_keys_kernel<<<blocks, 256, 0, st>>>(b.tmp, im.ranges, im.hdr, b.keys);
 }

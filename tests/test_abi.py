@@ -39,7 +39,7 @@ def test_version_and_layout_sizes():
     assert L.sfgs_version() == 1
     g1, g2 = L.sfgs_geom_bytes(1000), L.sfgs_geom_bytes(2000)
     assert 1000 * (64 + 24 + 1 + 4) <= g1 < g2
-    assert L.sfgs_image_bytes(1920, 1080) >= 1920 * 1080 * 4 + 8160 * 16
+    assert L.sfgs_image_bytes(1920, 1080) >= 1920 * 1080 * 4 + 8160 * 12   # n_contrib + ranges + tile histogram
     assert L.sfgs_binning_bytes(1000) >= 1000 * (4 + 1 + 8 + 8)
     assert L.sfgs_geom_bytes(0) > 0
 
