@@ -160,6 +160,18 @@ typedef struct sfgs_backward_args {
   /* optional: the forward's out_norm_raw.  When non-NULL, dL_dpix_norm is the gradient w.r.t. the UNIT normal
    * map and the blend adjoint applies the adjoint of F.normalize while it loads the pixel. */
   const float* norm_raw;
+  /* optional two-phase backward, for the tile-row sharded multi-GPU mode: the per-Gaussian
+   * blend-adjoint sums are linear in the pixel cotangents, so ranks exchange the [P,16] sums (64 B/Gaussian)
+   * instead of the final gradients (56+12M floats/Gaussian), and each rank finishes only its slice.
+   *   phase 0 (default)  both stages in one call; `acc` may be NULL (scratch comes from scratch_alloc).
+   *   phase 1            blend adjoint only: `acc` ([P,16] floats, caller-owned) is cleared and receives the sums
+   *                      of this rank's tile-row band; no gradient output is touched.
+   *   phase 2            per-Gaussian adjoint only, for Gaussians [gauss_begin, gauss_end): `acc` points at the
+   *                      row of Gaussian gauss_begin (e.g. the result of a reduce-scatter); gradient rows
+   *                      [gauss_begin, gauss_end) of the full-size output arrays are written, others untouched. */
+  int phase;
+  float* acc;
+  int gauss_begin, gauss_end;
 } sfgs_backward_args;
 
 int sfgs_rasterize_backward(const sfgs_backward_args* a);

@@ -41,7 +41,7 @@ int sfgs_launch_activations_bwd(int P, const float* opacity_raw, const float* sc
                                 const float* g_rotations, float* g_opacity_raw, float* g_scaling_raw,
                                 float* g_rotation_raw, cudaStream_t st);
 void sfgs_launch_gauss_bwd(const sfgs_backward_args* a, const GeomLayout& g, float focal_x, float focal_y,
-                           const float* acc, cudaStream_t st);
+                           const float* acc, int g_begin, int g_end, int acc_row0, cudaStream_t st);
 
 namespace {
 
@@ -266,19 +266,29 @@ int sfgs_rasterize_backward(const sfgs_backward_args* a) {
   if (!a) return fail(SFGS_E_BADARG, "backward: null args");
   if (a->P < 0 || a->width <= 0 || a->height <= 0) return fail(SFGS_E_BADARG, "backward: bad sizes");
   if (a->P == 0) return SFGS_OK;
+  const int phase = a->phase;
+  if (phase < 0 || phase > 2) return fail(SFGS_E_BADARG, "backward: phase must be 0, 1 or 2");
+  const bool do_blend = phase != 2, do_gauss = phase != 1;
   if (!a->geom_buffer || !a->binning_buffer || !a->image_buffer) return fail(SFGS_E_BADARG, "backward: null scratch buffer");
-  if (!a->dL_dpix || !a->dL_dpix_depth || !a->dL_dpix_norm || !a->dL_dpix_alpha || !a->accum_alphas)
+  if (do_blend && (!a->dL_dpix || !a->dL_dpix_depth || !a->dL_dpix_norm || !a->dL_dpix_alpha || !a->accum_alphas))
     return fail(SFGS_E_BADARG, "backward: null pixel gradient");
-  if (!a->dL_dmean2D || !a->dL_dconic || !a->dL_dopacity || !a->dL_dcolor || !a->dL_ddepth || !a->dL_dmean3D ||
-      !a->dL_dcov3D || !a->dL_dnorm3D || !a->dL_dscale || !a->dL_drot)
+  if (do_gauss && (!a->dL_dmean2D || !a->dL_dconic || !a->dL_dopacity || !a->dL_dcolor || !a->dL_ddepth || !a->dL_dmean3D ||
+                   !a->dL_dcov3D || !a->dL_dnorm3D || !a->dL_dscale || !a->dL_drot))
     return fail(SFGS_E_BADARG, "backward: null output");
-  if (a->M > 0 && a->shs && !a->dL_dsh) return fail(SFGS_E_BADARG, "backward: dL_dsh missing");
+  if (do_gauss && a->M > 0 && a->shs && !a->dL_dsh) return fail(SFGS_E_BADARG, "backward: dL_dsh missing");
   if (a->ED > 0 && (!a->dL_dextra || !a->dL_dpix_extra || !a->extra_attrs)) return fail(SFGS_E_BADARG, "backward: extra attrs missing");
-  if (!a->scratch_alloc) return fail(SFGS_E_BADARG, "backward: null scratch allocator");
+  if (phase != 0 && !a->acc) return fail(SFGS_E_BADARG, "backward: phases 1 and 2 need the caller's acc buffer");
+  if (phase == 0 && !a->acc && !a->scratch_alloc) return fail(SFGS_E_BADARG, "backward: null scratch allocator");
+  if (a->acc && (reinterpret_cast<uintptr_t>(a->acc) & 15)) return fail(SFGS_E_BADARG, "backward: acc must be 16-byte aligned");
   if (a->rotations && (reinterpret_cast<uintptr_t>(a->rotations) & 15)) return fail(SFGS_E_BADARG, "backward: rotations must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)a->stream;
   const bool debug = a->debug != 0;
   const int P = a->P;
+  int g_begin = 0, g_end = P;
+  if (phase == 2) {
+    g_begin = a->gauss_begin; g_end = a->gauss_end;
+    if (g_begin < 0 || g_end > P || g_begin > g_end) return fail(SFGS_E_BADARG, "backward: bad Gaussian range");
+  }
 
   GeomLayout g(sfgs_align_ptr(a->geom_buffer), (size_t)P);
   ImageLayout im(sfgs_align_ptr(a->image_buffer), a->width, a->height);
@@ -288,25 +298,33 @@ int sfgs_rasterize_backward(const sfgs_backward_args* a) {
   const float focal_y = a->height / (2.0f * a->tan_fovy);
   const float focal_x = a->width / (2.0f * a->tan_fovx);
 
-  const size_t abytes = (size_t)P * 16 * sizeof(float) + SFGS_ALIGN;
-  char* aptr = a->scratch_alloc(a->scratch_user, abytes);
-  if (!aptr) return fail(SFGS_E_ALLOC, "backward: scratch allocator returned NULL");
-  float* acc = (float*)sfgs_align_ptr(aptr);
-  PROF_BEGIN(ST_BWD_ZERO);
-  CU(cudaMemsetAsync(acc, 0, (size_t)P * 16 * sizeof(float), st));
-  if (a->ED > 0) CU(cudaMemsetAsync(a->dL_dextra, 0, (size_t)P * a->ED * sizeof(float), st));
-  PROF_END();
-
-  if (a->R > 0) {
-    PROF_BEGIN(ST_RENDER_BWD);
-    sfgs_launch_render_bwd(a, g, im, b, acc, st);
-    PROF_END();
-    STAGE_CHECK("render_bwd");
+  float* acc = a->acc;
+  if (!acc) {
+    const size_t abytes = (size_t)P * 16 * sizeof(float) + SFGS_ALIGN;
+    char* aptr = a->scratch_alloc(a->scratch_user, abytes);
+    if (!aptr) return fail(SFGS_E_ALLOC, "backward: scratch allocator returned NULL");
+    acc = (float*)sfgs_align_ptr(aptr);
   }
-  PROF_BEGIN(ST_GAUSS_BWD);
-  sfgs_launch_gauss_bwd(a, g, focal_x, focal_y, acc, st);
-  PROF_END();
-  STAGE_CHECK("gauss_bwd");
+  if (do_blend) {
+    // cleared right before the blend adjoint: the memset also makes the accumulator lines L2-resident for the
+    // kernel's vector reductions (clearing them earlier was measured to slow the NEXT kernel by 0.14 ms)
+    PROF_BEGIN(ST_BWD_ZERO);
+    CU(cudaMemsetAsync(acc, 0, (size_t)P * 16 * sizeof(float), st));
+    if (a->ED > 0) CU(cudaMemsetAsync(a->dL_dextra, 0, (size_t)P * a->ED * sizeof(float), st));
+    PROF_END();
+    if (a->R > 0) {
+      PROF_BEGIN(ST_RENDER_BWD);
+      sfgs_launch_render_bwd(a, g, im, b, acc, st);
+      PROF_END();
+      STAGE_CHECK("render_bwd");
+    }
+  }
+  if (do_gauss) {
+    PROF_BEGIN(ST_GAUSS_BWD);
+    sfgs_launch_gauss_bwd(a, g, focal_x, focal_y, acc, g_begin, g_end, phase == 2 ? g_begin : 0, st);
+    PROF_END();
+    STAGE_CHECK("gauss_bwd");
+  }
   return SFGS_OK;
 }
 

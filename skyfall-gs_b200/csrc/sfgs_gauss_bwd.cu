@@ -37,7 +37,7 @@ __device__ __forceinline__ float3 dnormvdv3(float3 v, float3 dv) {
 
 template <bool WRITE_SH>
 __global__ void __launch_bounds__(GB_THREADS, 5)
-gauss_bwd_kernel(int P, int D, int M, const float* __restrict__ means3D, const int* __restrict__ radii,
+gauss_bwd_kernel(int g_begin, int g_end, int acc_row0, int D, int M, const float* __restrict__ means3D, const int* __restrict__ radii,
                  const float* __restrict__ shs, const unsigned char* __restrict__ clamped,
                  const float* __restrict__ scales, const float* __restrict__ rotations, float scale_modifier,
                  const float* __restrict__ cov3Ds, const float* __restrict__ rec,
@@ -54,8 +54,8 @@ gauss_bwd_kernel(int P, int D, int M, const float* __restrict__ means3D, const i
   __shared__ unsigned short s_list[GB_SPAN];
   __shared__ int s_cnt[2 * GB_THREADS / 32];
   const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
-  const int base = blockIdx.x * GB_SPAN;
-  const int nspan = min(GB_SPAN, P - base);
+  const int base = g_begin + blockIdx.x * GB_SPAN;           // Gaussians [g_begin, g_end) are this launch's share
+  const int nspan = min(GB_SPAN, g_end - base);
 
   // ---------------- phase A: which Gaussians of the span were rasterized ----------------
   // Culled Gaussians (64 % of the 1M-Gaussian benchmark frame) only need zeros.  Running the adjoint chain
@@ -143,7 +143,7 @@ gauss_bwd_kernel(int P, int D, int M, const float* __restrict__ means3D, const i
       scx = scales[3 * i]; scy = scales[3 * i + 1]; scz = scales[3 * i + 2];
     }
     const unsigned cm = shs != nullptr ? clamped[idx] : 0u;
-    const float4* a4 = reinterpret_cast<const float4*>(acc + i * 16);
+    const float4* a4 = reinterpret_cast<const float4*>(acc + (i - (size_t)acc_row0) * 16);
     const float4 A0 = a4[0], A1 = a4[1], A2 = a4[2], A3 = a4[3];
     const float4 rec1 = *reinterpret_cast<const float4*>(rec + i * REC_FLOATS + 4);    // con.z, opacity*coef, depth
     const float4 rec2 = *reinterpret_cast<const float4*>(rec + i * REC_FLOATS + 8);    // r, g, b, nx
@@ -459,20 +459,17 @@ gauss_bwd_kernel(int P, int D, int M, const float* __restrict__ means3D, const i
 }  // namespace
 
 void sfgs_launch_gauss_bwd(const sfgs_backward_args* a, const GeomLayout& g, float focal_x, float focal_y,
-                           const float* acc, cudaStream_t st) {
-  const int blocks = (a->P + GB_SPAN - 1) / GB_SPAN;
+                           const float* acc, int g_begin, int g_end, int acc_row0, cudaStream_t st) {
+  if (g_end <= g_begin) return;
+  const int blocks = (g_end - g_begin + GB_SPAN - 1) / GB_SPAN;
   const float* cov3D_ptr = a->cov3D_precomp != nullptr ? a->cov3D_precomp : g.cov3D;
   SFGS_COUNT_LAUNCH();
-  if (a->M > 0 && a->dL_dsh != nullptr)
-    gauss_bwd_kernel<true><<<blocks, GB_THREADS, 0, st>>>(
-        a->P, a->D, a->M, a->means3D, a->radii, a->shs, g.clamped, a->scales, a->rotations, a->scale_modifier,
-        cov3D_ptr, g.rec, a->norm3D_precomp, a->viewmatrix, a->projmatrix, focal_x, focal_y, a->tan_fovx,
-        a->tan_fovy, a->kernel_size, a->cam_pos, acc, a->dL_dmean2D, a->dL_dconic, a->dL_dopacity, a->dL_dcolor,
-        a->dL_ddepth, a->dL_dmean3D, a->dL_dcov3D, a->dL_dnorm3D, a->dL_dsh, a->dL_dscale, a->dL_drot);
-  else
-    gauss_bwd_kernel<false><<<blocks, GB_THREADS, 0, st>>>(
-        a->P, a->D, 0, a->means3D, a->radii, nullptr, g.clamped, a->scales, a->rotations, a->scale_modifier,
-        cov3D_ptr, g.rec, a->norm3D_precomp, a->viewmatrix, a->projmatrix, focal_x, focal_y, a->tan_fovx,
-        a->tan_fovy, a->kernel_size, a->cam_pos, acc, a->dL_dmean2D, a->dL_dconic, a->dL_dopacity, a->dL_dcolor,
-        a->dL_ddepth, a->dL_dmean3D, a->dL_dcov3D, a->dL_dnorm3D, nullptr, a->dL_dscale, a->dL_drot);
+#define GB_ARGS                                                                                                       \
+  g_begin, g_end, acc_row0, a->D, a->M, a->means3D, a->radii, a->shs, g.clamped, a->scales, a->rotations,             \
+      a->scale_modifier, cov3D_ptr, g.rec, a->norm3D_precomp, a->viewmatrix, a->projmatrix, focal_x, focal_y,         \
+      a->tan_fovx, a->tan_fovy, a->kernel_size, a->cam_pos, acc, a->dL_dmean2D, a->dL_dconic, a->dL_dopacity,         \
+      a->dL_dcolor, a->dL_ddepth, a->dL_dmean3D, a->dL_dcov3D, a->dL_dnorm3D, a->dL_dsh, a->dL_dscale, a->dL_drot
+  if (a->M > 0 && a->dL_dsh != nullptr) gauss_bwd_kernel<true><<<blocks, GB_THREADS, 0, st>>>(GB_ARGS);
+  else gauss_bwd_kernel<false><<<blocks, GB_THREADS, 0, st>>>(GB_ARGS);
+#undef GB_ARGS
 }

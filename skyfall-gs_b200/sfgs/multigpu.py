@@ -9,8 +9,13 @@ scripts/run_jax.py:52-87).  Design:
 * forward: each rank runs the normal pipeline restricted to its band (`tile_rows=` of
   sfgs.rasterizer.rasterize_gaussians), then ONE all_gather of the 8 image planes of the bands
   (padded to the tallest band) assembles the frame on every rank;
-* backward: each rank back-propagates its band's pixels; per-Gaussian gradients are partial sums over
-  bands, combined with ONE all_reduce(sum) (replicated parameters).
+* backward: each rank runs the blend adjoint of its band only (`phase=1` of
+  sfgs.rasterizer.rasterize_gaussians_backward).  The per-Gaussian adjoint is linear in the 14 blend-adjoint
+  sums, so the ranks exchange those ([P,16] floats, 64 B/Gaussian) instead of the final gradients
+  ((14+3M)·4 = 248 B/Gaussian at M=16): ONE reduce_scatter(sum) hands every rank the complete sums of its
+  slice of Gaussians (`gaussian_slices`), and it finishes only that slice (`phase=2`) — the sharded-optimizer
+  layout.  `reduce_gradients` (all_reduce of the final gradients, replicated parameters) remains as the simple
+  alternative.
 
 The host logic (partitioning, padded gather/assembly, reduction) is backend-agnostic and covered by
 world-size-2 gloo tests on CPU tensors; on B200s the backend is NCCL over NVLink/NVSwitch.
@@ -93,6 +98,31 @@ def reduce_gradients(grads: Sequence[torch.Tensor], group=None) -> None:
         off += n
 
 
+def gaussian_slices(P: int, world: int) -> List[int]:
+    """Equal slices of the Gaussian index range for the per-Gaussian adjoint: world+1 boundaries, slice length
+    ceil(P/world) (the last one may be shorter or empty)."""
+    per = (P + world - 1) // world
+    return [min(g * per, P) for g in range(world + 1)]
+
+
+def reduce_scatter_sums(acc: torch.Tensor, group=None) -> torch.Tensor:
+    """acc: this rank's partial [P,16] blend-adjoint sums.  Returns the complete sums of this rank's slice
+    ([ceil(P/world),16]; rows past P are zero).  NCCL: one reduce_scatter; backends without it (gloo): all_reduce
+    + slice."""
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    P = acc.shape[0]
+    per = (P + world - 1) // world
+    if per * world != P:
+        acc = torch.cat([acc, acc.new_zeros((per * world - P, acc.shape[1]))], 0)
+    if dist.get_backend(group) == "nccl":
+        out = torch.empty((per, acc.shape[1]), dtype=acc.dtype, device=acc.device)
+        dist.reduce_scatter_tensor(out, acc.contiguous(), op=dist.ReduceOp.SUM, group=group)
+        return out
+    full = acc.clone()
+    dist.all_reduce(full, op=dist.ReduceOp.SUM, group=group)
+    return full[rank * per:(rank + 1) * per].contiguous()
+
+
 def row_histogram(ranges: torch.Tensor, tiles_x: int) -> List[int]:
     """Instances per tile row from the image buffer's `ranges` [tiles,2]."""
     cnt = (ranges[:, 1] - ranges[:, 0]).long().view(-1, tiles_x).sum(1)
@@ -134,16 +164,26 @@ def bench_tilerows(args, rank, world, dev, steps, warmup, metric):
     cuts = partition_rows(row_histogram(ranges, tiles_x), world)
     band = (cuts[rank], cuts[rank + 1])
 
+    sl = gaussian_slices(scene.P, world)
+    per = sl[1] - sl[0]
+    acc_buf = torch.empty((per * world, 16), dtype=torch.float32, device=dev)   # padded to equal slices
+    acc_buf[scene.P:].zero_()
+
+    def bwd(f, **kw):
+        return R.rasterize_gaussians_backward(d["bg"], d["means3D"], f[5], e, d["scales"], d["rotations"], e, 1.0, e, e,
+                                              d["view"], d["proj"], cam.tanfovx, cam.tanfovy, 0.1, cot[0], cot[1],
+                                              cot[2], cot[3], e, d["shs"], 3, d["campos"], f[7], f[0], f[8], f[9], f[4],
+                                              False, tile_rows=band, **kw)
+
     def step():
         f = fwd(band)
         planes = torch.cat([f[1], f[2], f[4], f[3]], 0)            # colour, depth, alpha, normal: 8 planes
         full = gather_bands(planes, cuts, H)
-        g = R.rasterize_gaussians_backward(d["bg"], d["means3D"], f[5], e, d["scales"], d["rotations"], e, 1.0, e, e,
-                                           d["view"], d["proj"], cam.tanfovx, cam.tanfovy, 0.1, cot[0], cot[1], cot[2],
-                                           cot[3], e, d["shs"], 3, d["campos"], f[7], f[0], f[8], f[9], f[4], False,
-                                           tile_rows=band)
-        reduce_gradients([g[3], g[0], g[6], g[2], g[7], g[8]])
-        return full
+        bwd(f, phase=1, acc=acc_buf[:scene.P])                      # blend adjoint of this band -> partial sums
+        mine = torch.empty((per, 16), dtype=torch.float32, device=dev)
+        dist.reduce_scatter_tensor(mine, acc_buf, op=dist.ReduceOp.SUM)
+        g = bwd(f, phase=2, acc=mine, gauss_range=(sl[rank], sl[rank + 1]))   # finish this rank's slice only
+        return full, g
 
     for _ in range(warmup):
         step()
@@ -164,7 +204,10 @@ def bench_tilerows(args, rank, world, dev, steps, warmup, metric):
                           "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": round(total / steps, 4),
                           "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
                           "data": "synthetic",
-                          "config": {"workload": "one 1920x1080 frame of the 1M-Gaussian scene sharded by tile rows",
-                                     "parallelism": f"tilerows x{world}: image all_gather + gradient all_reduce (NCCL)",
+                          "config": {"workload": f"one 1920x1080 frame of the {scene.P}-Gaussian scene sharded by tile rows",
+                                     "P": scene.P,
+                                     "parallelism": f"tilerows x{world}: image all_gather + reduce_scatter of the "
+                                                    "[P,16] blend-adjoint sums (NCCL); each rank finishes the "
+                                                    "gradients of P/N Gaussians",
                                      "cuts": cuts, "l2": "not flushed (collectives in the loop)"}}))
     dist.destroy_process_group()

@@ -64,6 +64,7 @@ class BackwardArgs(C.Structure):
         ("debug", C.c_int), ("stream", C.c_void_p),
         ("tile_row_begin", C.c_int), ("tile_row_end", C.c_int),
         ("norm_raw", c_float_p),
+        ("phase", C.c_int), ("acc", c_float_p), ("gauss_begin", C.c_int), ("gauss_end", C.c_int),
     ]
 
 

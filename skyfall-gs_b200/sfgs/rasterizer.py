@@ -127,10 +127,16 @@ def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rot
                                  cov3Ds_precomp, norm3Ds_precomp, viewmatrix, projmatrix, tan_fovx, tan_fovy,
                                  kernel_size, dL_dout_color, dL_dout_depth, dL_dout_norm, dL_dout_alpha,
                                  dL_dout_extra, sh, degree, campos, geomBuffer, R, binningBuffer, imageBuffer,
-                                 out_alpha, debug, tile_rows=None, norm_raw=None):
+                                 out_alpha, debug, tile_rows=None, norm_raw=None, phase=0, acc=None,
+                                 gauss_range=None):
     """Same positional signature and return tuple as the reference's `_C.rasterize_gaussians_backward`.  With
     `norm_raw` (the extra tensor a `fuse_normalize=True` forward returned) `dL_dout_norm` is taken w.r.t. the unit
-    normal map and the adjoint of F.normalize is applied inside the blend-adjoint kernel."""
+    normal map and the adjoint of F.normalize is applied inside the blend-adjoint kernel.
+
+    Two-phase form for the tile-row sharded multi-GPU mode (include/sfgs.h): `phase=1` runs only the blend adjoint
+    of this rank's band and returns the [P,16] sums (`acc`, allocated here unless given); `phase=2` runs only the
+    per-Gaussian adjoint for `gauss_range=(begin, end)` from `acc`, whose row 0 is Gaussian `begin` (e.g. a
+    reduce-scatter result), and returns the usual tuple with rows [begin, end) valid."""
     L = N.lib()
     P = int(means3D.shape[0])
     H, W = int(dL_dout_color.shape[1]), int(dL_dout_color.shape[2])
@@ -158,6 +164,13 @@ def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rot
         scratch = _Arena(dev)
         keep = []
         a = N.BackwardArgs()
+        a.phase = int(phase)
+        if phase == 1 and acc is None:
+            acc = torch.empty((P, 16), **fopt)
+        if acc is not None:
+            a.acc = _ptr(acc, keep)
+        if gauss_range is not None:
+            a.gauss_begin, a.gauss_end = int(gauss_range[0]), int(gauss_range[1])
         a.P, a.D, a.M, a.R, a.ED = P, int(degree), M, int(R), F
         a.width, a.height = W, H
         a.background = _ptr(background, keep)
@@ -203,6 +216,8 @@ def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rot
         if tile_rows is not None:
             a.tile_row_begin, a.tile_row_end = int(tile_rows[0]), int(tile_rows[1])
         N.check(L.sfgs_rasterize_backward(C.byref(a)), "sfgs_rasterize_backward")
+    if phase == 1:
+        return acc
     return (outs["means2D"], outs["colors"], outs["opacity"], outs["means3D"], outs["cov3D"], outs["norm3D"],
             dL_dsh, outs["scales"], outs["rot"], dL_dextra)
 

@@ -26,7 +26,8 @@ def run_ours_forward(d, cam, sh_degree, bg, kernel_size=0.1, scale_modifier=1.0,
     return dict(zip(keys, out))
 
 
-def run_ours_backward(d, cam, sh_degree, bg, fwd, cot, kernel_size=0.1, scale_modifier=1.0, colors=None, debug=False):
+def run_ours_backward(d, cam, sh_degree, bg, fwd, cot, kernel_size=0.1, scale_modifier=1.0, colors=None, debug=False,
+                      **kw):
     from sfgs import rasterizer as R
     e = torch.empty(0, device=d["means3D"].device)
     sh = e if colors is not None else d["shs"]
@@ -35,7 +36,9 @@ def run_ours_backward(d, cam, sh_degree, bg, fwd, cot, kernel_size=0.1, scale_mo
                                          scale_modifier, e, e, d["viewmatrix"], d["projmatrix"], cam.tanfovx,
                                          cam.tanfovy, kernel_size, cot[0], cot[1], cot[2], cot[3], e, sh, sh_degree,
                                          d["campos"], fwd["geom"], fwd["num_rendered"], fwd["binning"], fwd["img"],
-                                         fwd["alpha"], debug)
+                                         fwd["alpha"], debug, **kw)
+    if kw.get("phase") == 1:
+        return out                      # the [P,16] blend-adjoint sums
     keys = ("means2D", "colors", "opacity", "means3D", "cov3D", "norm3D", "sh", "scales", "rot", "extra")
     return dict(zip(keys, out))
 

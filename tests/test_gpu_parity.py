@@ -315,6 +315,30 @@ def test_fused_normalize_matches_torch_post_op(cuda_device, monkeypatch):
     assert (m_f - m_t).abs().max().item() <= 1e-5 + 2e-4 * m_t.abs().max().item()
 
 
+def test_two_phase_backward_equals_single_call(cuda_device):
+    """Multi-GPU building block on one GPU: blend adjoint (phase 1) -> [P,16] sums -> per-Gaussian adjoint of two
+    Gaussian slices (phase 2, each fed only its slice of the sums) reproduces the one-call backward."""
+    dev = cuda_device
+    scene, cam = S.blob_scene(5000, seed=91), S.simple_camera(256, 144)
+    d = Hh.to_torch(scene, cam, dev)
+    bg = torch.tensor([0.3, 0.2, 0.1], device=dev)
+    cot = [torch.from_numpy(c).to(dev) for c in S.cotangents(cam.width, cam.height, seed=4)]
+    f = Hh.run_ours_forward(d, cam, 3, bg)
+    ref = Hh.run_ours_backward(d, cam, 3, bg, f, cot)
+    acc = Hh.run_ours_backward(d, cam, 3, bg, f, cot, phase=1)
+    assert acc.shape == (scene.P, 16)
+    cut = 2173                                                   # deliberately not a multiple of the block span
+    parts = [Hh.run_ours_backward(d, cam, 3, bg, f, cot, phase=2, acc=acc[a:b].clone(), gauss_range=(a, b))
+             for a, b in ((0, cut), (cut, scene.P))]
+    for k in ref:
+        if ref[k].numel() == 0:
+            continue
+        got = torch.cat([parts[0][k][:cut], parts[1][k][cut:]], 0)
+        assert got.shape == ref[k].shape
+        tol = 1e-5 + 2e-4 * ref[k].abs().max().item()         # the sums themselves carry the reductions' order noise
+        assert (got - ref[k]).abs().max().item() <= tol, k
+
+
 def test_mark_visible_matches_oracle(cuda_device):
     from oracle import cpu_oracle as O
     from sfgs import rasterizer as R

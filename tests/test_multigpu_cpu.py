@@ -26,6 +26,7 @@ def test_partition_rows_balanced_and_total():
     # uniform weights -> equal split
     assert MG.partition_rows([1] * 68, 4) == [0, 17, 34, 51, 68]
     assert MG.tile_rows(1080) == 68 and MG.band_pixel_rows([0, 34, 68], 1, 1080) == (544, 1080)
+    assert MG.gaussian_slices(10, 4) == [0, 3, 6, 9, 10] and MG.gaussian_slices(2, 4) == [0, 1, 2, 2, 2]
 
 
 def _free_port():
@@ -52,7 +53,17 @@ def _worker(rank, world, port, out):
         g2 = torch.full((5,), 10.0 * (rank + 1))
         MG.reduce_gradients([g1, g2])
         ok_reduce = bool(torch.all(g1 == 3.0)) and bool(torch.all(g2 == 30.0))
-        out.put((rank, ok_gather, ok_reduce))
+        # blend-adjoint sums: P = 7 Gaussians over 2 ranks -> slices [0,4) and [4,7); every rank ends up with the
+        # complete sums of its own slice only (zero rows past P)
+        P = 7
+        acc = torch.arange(P * 16, dtype=torch.float32).view(P, 16) * (rank + 1)
+        mine = MG.reduce_scatter_sums(acc)
+        sl = MG.gaussian_slices(P, world)
+        want = torch.zeros((4, 16))
+        n = sl[rank + 1] - sl[rank]
+        want[:n] = torch.arange(P * 16, dtype=torch.float32).view(P, 16)[sl[rank]:sl[rank + 1]] * 3.0
+        ok_rs = sl == [0, 4, 7] and mine.shape == (4, 16) and bool(torch.equal(mine, want))
+        out.put((rank, ok_gather, ok_reduce and ok_rs))
     finally:
         dist.destroy_process_group()
 
