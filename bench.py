@@ -457,15 +457,21 @@ def main():
         ach = alg[dom] / (stage_ms[dom] / 1e3) / 1e9
         b_total = sum(alg.values())
         t_kernels = sum(stage_ms.values())
-        traffic = None
+        traffic, issue = None, None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")   # dram__bytes_read+write per launch from `ncu --set full`
         if os.path.exists(tpath):
             with open(tpath) as f:
-                traffic = json.load(f).get("kernels", {}).get(dom)
+                tj = json.load(f)
+            traffic = tj.get("kernels", {}).get(dom)
+            issue = tj.get("issue_slots_active_pct", {}).get(dom)
         out["roofline"] = {"bound": "hbm", "kernel": dom, "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
                            "frac": round(ach / peak, 4), "traffic": traffic, "peak_source": peak_src,
                            "algorithmic_bytes": int(alg[dom]), "kernel_ms": round(stage_ms[dom], 4),
                            "share_of_step": round(stage_ms[dom] / t_kernels, 3)}
+        if issue is not None:
+            # the blend kernels are bound by instruction issue, not by HBM: say so next to the HBM fraction
+            out["roofline"]["limiter"] = (f"instruction issue: {issue}% of issue slots active (ncu, "
+                                          "profiles/r1e_all_kernels_full.md); DRAM traffic is the `traffic` field")
         out["roofline_pipeline"] = {"algorithmic_bytes": int(b_total), "kernels_ms": round(t_kernels, 4),
                                     "achieved": round(b_total / (t_kernels / 1e3) / 1e9, 1), "unit": "GB/s",
                                     "frac": round(b_total / (t_kernels / 1e3) / 1e9 / peak, 4)}
