@@ -42,6 +42,7 @@ int sfgs_launch_activations_bwd(int P, const float* opacity_raw, const float* sc
                                 float* g_rotation_raw, cudaStream_t st);
 void sfgs_launch_gauss_bwd(const sfgs_backward_args* a, const GeomLayout& g, float focal_x, float focal_y,
                            const float* acc, int g_begin, int g_end, int acc_row0, cudaStream_t st);
+void sfgs_launch_acc_clear_visible(int P, const int* radii, float* acc, cudaStream_t st);
 
 namespace {
 
@@ -309,7 +310,10 @@ int sfgs_rasterize_backward(const sfgs_backward_args* a) {
     // cleared right before the blend adjoint: the memset also makes the accumulator lines L2-resident for the
     // kernel's vector reductions (clearing them earlier was measured to slow the NEXT kernel by 0.14 ms)
     PROF_BEGIN(ST_BWD_ZERO);
-    CU(cudaMemsetAsync(acc, 0, (size_t)P * 16 * sizeof(float), st));
+    // one call: only rows of rasterized Gaussians are ever accumulated into or read; two-phase: the caller sums
+    // whole buffers across ranks, so every row must be defined
+    if (phase == 0 && a->radii) sfgs_launch_acc_clear_visible(P, a->radii, acc, st);
+    else CU(cudaMemsetAsync(acc, 0, (size_t)P * 16 * sizeof(float), st));
     if (a->ED > 0) CU(cudaMemsetAsync(a->dL_dextra, 0, (size_t)P * a->ED * sizeof(float), st));
     PROF_END();
     if (a->R > 0) {

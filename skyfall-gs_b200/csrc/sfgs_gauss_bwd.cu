@@ -52,6 +52,7 @@ gauss_bwd_kernel(int g_begin, int g_end, int acc_row0, int D, int M, const float
   // (fast path), or 19 floats of per-thread scratch for the generic dL_dsh store
   __shared__ __align__(128) float s_tile[WRITE_SH ? GB_THREADS * 48 : 4];
   __shared__ unsigned short s_list[GB_SPAN];
+  __shared__ unsigned char s_vis[GB_SPAN];
   __shared__ int s_cnt[2 * GB_THREADS / 32];
   const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
   const int base = g_begin + blockIdx.x * GB_SPAN;           // Gaussians [g_begin, g_end) are this launch's share
@@ -68,6 +69,7 @@ gauss_bwd_kernel(int g_begin, int g_end, int acc_row0, int D, int M, const float
     const int g = r * GB_THREADS + t;
     vis[r] = g < nspan && radii[base + g] > 0;
     bal[r] = __ballot_sync(0xffffffffu, vis[r]);
+    s_vis[g] = vis[r] ? 1 : 0;
     if (lane == 0) s_cnt[r * (GB_THREADS / 32) + wid] = __popc(bal[r]);
   }
   __syncthreads();
@@ -103,7 +105,19 @@ gauss_bwd_kernel(int g_begin, int g_end, int acc_row0, int D, int M, const float
     zero_fill(dL_dnorm3D, 3);
     zero_fill(dL_dscale, 3);
     zero_fill(dL_drot, 4);
-    if (WRITE_SH) zero_fill(dL_dsh, 3 * M);
+    if (WRITE_SH) {
+      // dL_dsh is 2/3 of the output bytes: its rows are whole 16-byte units when M is a multiple of 4 and the
+      // buffer is aligned, so the rows the dense warps are about to write anyway are skipped
+      float* d = dL_dsh + (size_t)base * 3 * M;
+      if ((M & 3) == 0 && (reinterpret_cast<uintptr_t>(d) & 15) == 0) {
+        const int q_per_row = 3 * M / 4, nq = nspan * q_per_row;
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = t; i < nq; i += GB_THREADS)
+          if (!s_vis[i / q_per_row]) reinterpret_cast<float4*>(d)[i] = z;
+      } else {
+        zero_fill(dL_dsh, 3 * M);
+      }
+    }
   }
   __syncthreads();   // orders the zero fill before the row stores below, and publishes s_list
 
@@ -457,6 +471,24 @@ gauss_bwd_kernel(int g_begin, int g_end, int acc_row0, int D, int M, const float
 }
 
 }  // namespace
+
+// Clears the [P,16] accumulator rows of rasterized Gaussians only (the blend adjoint touches no other row and the
+// per-Gaussian adjoint reads no other row): 64 B x V instead of a 64 B x P memset, and less of the L2 spent on rows
+// nobody will use.  Runs right before the blend adjoint, so the lines it writes are L2-resident for the reductions.
+namespace {
+__global__ void __launch_bounds__(256)
+acc_clear_visible_kernel(int P, const int* __restrict__ radii, float* __restrict__ acc) {
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= P || radii[i] <= 0) return;
+  float4* a = reinterpret_cast<float4*>(acc + (size_t)i * 16);
+  a[0] = a[1] = a[2] = a[3] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+}  // namespace
+
+void sfgs_launch_acc_clear_visible(int P, const int* radii, float* acc, cudaStream_t st) {
+  SFGS_COUNT_LAUNCH();
+  acc_clear_visible_kernel<<<(P + 255) / 256, 256, 0, st>>>(P, radii, acc);
+}
 
 void sfgs_launch_gauss_bwd(const sfgs_backward_args* a, const GeomLayout& g, float focal_x, float focal_y,
                            const float* acc, int g_begin, int g_end, int acc_row0, cudaStream_t st) {
