@@ -209,17 +209,17 @@ def measure(step_fn, steps, warmup, flush, dev, between=None, max_attempts=5):
     Every step launches ~10 kernels from Python and the forward waits once for the instance count, so a host
     core that is descheduled for a few ms leaves the GPU idle inside the timed step; the boxes are shared
     (load average 40-60 on 128 cores observed) and single steps of 5-250 ms appear at random in either leg.
-    A pass counts as clean when its MEAN step is within 10 % of its fastest step (one large spike is enough to
+    A pass counts as clean when its MEAN step is within 5 % of its fastest step (one large spike is enough to
     fail it); the reported pass is the first clean one, or the pass with the smallest total if none of
     `max_attempts` is.  Every attempt is listed in the JSON line."""
     attempts = []
     for k in range(max_attempts):
         ms = timed_steps(step_fn, steps, warmup if k == 0 else 3, flush, dev, between)
         attempts.append(ms)
-        if sum(ms) / len(ms) <= 1.10 * min(ms):
+        if sum(ms) / len(ms) <= 1.05 * min(ms):
             break
     best = min(attempts, key=sum)
-    if sum(attempts[-1]) / len(attempts[-1]) <= 1.10 * min(attempts[-1]):
+    if sum(attempts[-1]) / len(attempts[-1]) <= 1.05 * min(attempts[-1]):
         best = attempts[-1]
     info = {"attempts": len(attempts), "ms_per_step_of_each_attempt": [round(sum(a) / len(a), 4) for a in attempts],
             "reported_min_ms": round(min(best), 4), "reported_median_ms": round(sorted(best)[len(best) // 2], 4)}
@@ -265,8 +265,8 @@ class E2EOurs:
                                                           rotations=rots)
         cur.wait_stream(self.copy_stream)
         gt.record_stream(cur)
-        gt = gt.to(torch.float32).mul_(1.0 / 255.0)
-        loss = (color - gt).abs().mean() + 0.01 * depth.mean() + 0.01 * (1 - alpha).mean() + 0.01 * norm.mean()
+        gt = torch.mul(gt, 1.0 / 255.0)          # uint8 -> float32 in [0,1], one kernel
+        loss = torch.nn.functional.l1_loss(color, gt) + 0.01 * depth.mean() + 0.01 * (1 - alpha).mean() + 0.01 * norm.mean()
         for p in self.params:
             p.grad = None
         self.means2D.grad = None
@@ -303,11 +303,11 @@ class E2ERef:
                              proj, cam.tanfovx, cam.tanfovy, 0.1, cam.height, cam.width, d["shs"], SH_DEGREE, campos)
         cur.wait_stream(self.copy_stream)
         gt.record_stream(cur)
-        gt = gt.to(torch.float32).mul_(1.0 / 255.0)
+        gt = torch.mul(gt, 1.0 / 255.0)          # uint8 -> float32 in [0,1], one kernel
         n = float(cam.height * cam.width)
         norm_raw = f["norm"].detach().requires_grad_(True)
         norm = torch.nn.functional.normalize(norm_raw, p=2, dim=0)
-        loss = (f["color"] - gt).abs().mean() + 0.01 * f["depth"].mean() + 0.01 * (1 - f["alpha"]).mean() + 0.01 * norm.mean()
+        loss = torch.nn.functional.l1_loss(f["color"], gt) + 0.01 * f["depth"].mean() + 0.01 * (1 - f["alpha"]).mean() + 0.01 * norm.mean()
         (g_norm,) = torch.autograd.grad(0.01 * norm.mean(), norm_raw)
         g_color = torch.sign(f["color"] - gt) / (3 * n)
         g_depth = torch.full_like(f["depth"], 0.01 / n)
@@ -427,7 +427,7 @@ def main():
                    "d2h_bytes_per_step": 4},
            "clocks": clocks}
     out["timing"] = {"value": value_info, "e2e": e2e_info,
-                     "rule": "a pass whose mean step exceeds 1.10x its fastest step is re-measured (<= 5 passes)"}
+                     "rule": "a pass whose mean step exceeds 1.05x its fastest step is re-measured (<= 5 passes)"}
     out["e2e"]["api"] = ("diff_gauss.GaussianRasterizer + autograd" if args.impl == "ours"
                          else "reference CudaRasterizer::Rasterizer forward/backward")
     if args.impl == "ours":
