@@ -87,6 +87,14 @@ def _wrap(ptr, shape, dtype, device):
     return out
 
 
+def _order(dev):
+    """The reference launches on the legacy default stream, like torch's default stream: same-stream ordering needs
+    no host synchronisation.  Only when the caller switched torch to another stream is a full sync required."""
+    cur = torch.cuda.current_stream(dev)
+    if cur != torch.cuda.default_stream(dev):
+        torch.cuda.synchronize(dev)
+
+
 def forward(bg, means3D, colors, opacity, scales, rotations, scale_modifier, cov3D_precomp, norm3D_precomp, extra,
             viewmatrix, projmatrix, tan_fovx, tan_fovy, kernel_size, H, W, sh, degree, campos, prefiltered=False,
             debug=False):
@@ -103,7 +111,7 @@ def forward(bg, means3D, colors, opacity, scales, rotations, scale_modifier, cov
     radii = torch.zeros((P,), dtype=torch.int32, device=dev)
     out_extra = torch.zeros((F, H, W), **f) if F else torch.empty(0, **f)
     g, b, i = _Arena(dev), _Arena(dev), _Arena(dev)
-    torch.cuda.synchronize(dev)
+    _order(dev)
     with torch.cuda.device(dev):
         R = L.ref_forward(g.cb, None, b.cb, None, i.cb, None, P, int(degree), M, F, _p(bg), W, H, _p(means3D), _p(sh),
                           _p(colors), _p(opacity), _p(scales), float(scale_modifier), _p(rotations),
@@ -111,7 +119,7 @@ def forward(bg, means3D, colors, opacity, scales, rotations, scale_modifier, cov
                           _p(campos), float(tan_fovx), float(tan_fovy), float(kernel_size), int(prefiltered),
                           _p(out_color), _p(out_depth), _p(out_norm), _p(out_alpha), _p(out_extra), _p(radii),
                           int(debug))
-    torch.cuda.synchronize(dev)
+    _order(dev)
     if R < 0:
         raise RuntimeError("reference forward threw")
     return dict(num_rendered=R, color=out_color, depth=out_depth, norm=out_norm, alpha=out_alpha, radii=radii,
@@ -131,7 +139,7 @@ def backward(bg, means3D, radii, colors, scales, rotations, extra, scale_modifie
     o = dict(means3D=z(P, 3), means2D=z(P, 3), colors=z(P, 3), depths=z(P, 1), conic=z(P, 2, 2), opacity=z(P, 1),
              cov3D=z(P, 6), norm3D=z(P, 3), sh=z(P, M, 3), scales=z(P, 3), rot=z(P, 4),
              extra=z(P, F) if F else torch.empty(0, device=dev))
-    torch.cuda.synchronize(dev)
+    _order(dev)
     with torch.cuda.device(dev):
         rc = L.ref_backward(P, int(degree), M, int(R), F, _p(bg), W, H, _p(means3D), _p(sh), _p(colors), _p(scales),
                             float(scale_modifier), _p(rotations), _p(cov3D_precomp), _p(norm3D_precomp), _p(extra),
@@ -142,7 +150,7 @@ def backward(bg, means3D, radii, colors, scales, rotations, extra, scale_modifie
                             _p(o["means2D"]), _p(o["conic"]), _p(o["opacity"]), _p(o["colors"]), _p(o["depths"]),
                             _p(o["means3D"]), _p(o["cov3D"]), _p(o["norm3D"]), _p(o["sh"]), _p(o["scales"]),
                             _p(o["rot"]), _p(o["extra"]), int(debug))
-    torch.cuda.synchronize(dev)
+    _order(dev)
     if rc != 0:
         raise RuntimeError("reference backward threw")
     return o
@@ -181,16 +189,16 @@ def mark_visible(means3D, viewmatrix, projmatrix):
     L = lib()
     P = means3D.shape[0]
     present = torch.zeros((P,), dtype=torch.bool, device=means3D.device)
-    torch.cuda.synchronize()
+    _order(None)
     L.ref_mark_visible(P, _p(means3D), _p(viewmatrix), _p(projmatrix), _p(present))
-    torch.cuda.synchronize()
+    _order(None)
     return present
 
 
 def knn(points):
     L = lib()
     out = torch.zeros((points.shape[0],), dtype=torch.float32, device=points.device)
-    torch.cuda.synchronize()
+    _order(None)
     L.ref_knn(points.shape[0], _p(points.contiguous()), _p(out))
-    torch.cuda.synchronize()
+    _order(None)
     return out
