@@ -117,53 +117,71 @@ scatter_keys_kernel(const uint4* __restrict__ tmp, const uint2* __restrict__ ran
 }
 
 // ---- per-tile sort -------------------------------------------------------------
-// One CTA per tile, two launches over the same grid: a light variant (128 threads, 1024-key window) for
-// the common short lists and a heavy one (256 threads, 4096-key window, global radix fallback beyond that);
-// a CTA whose tile belongs to the other class exits at once.  Lists inside the window are sorted with a
-// Bitonic network on the n 64-bit (depth_bits << 32 | id) keys of one tile, n2 = next power of two >= n.
-//
-// The network is the "all comparators ascending" form: round k first pairs element t of every k-block with its
-// mirror k-1-t, then runs the usual strides k/4 .. 1.  With every comparator ascending, keys at positions >= n
-// behave as +inf that never move, so a comparator whose upper index is >= n is simply skipped: nothing is padded
-// and the work per stage is ~n/2 exchanges instead of n2/2 (tiles average ~280 keys, i.e. n2 = 512).
-//
-// Exchange i of a stage touches two keys of the aligned 2*j-block that contains 2*i (j = k/2 for the mirror
-// stage).  For j <= 32 the 32 exchanges of one warp stay inside one aligned 64-key block, so consecutive stages
-// with j <= 32 only need __syncwarp(); block-wide barriers remain for the strides j >= 64.
-template <int THREADS>
-__device__ __forceinline__ void bitonic_smem(uint64_t* s, int n, int n2) {
-  const int half = n2 >> 1;
-  for (int k = 2; k <= n2; k <<= 1) {
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      if (j == (k >> 1)) {
-        const int lim = min(half, (n >> 1) + (k >> 2) + 1);   // exchanges beyond this have hi >= n
-        for (int i = threadIdx.x; i < lim; i += THREADS) {
-          const int t = i & (j - 1);
-          const int blk = (i - t) << 1;                        // first key of the k-block
-          const int lo = blk + t, hi = blk + k - 1 - t;
-          if (hi < n) {
-            const uint64_t a = s[lo], b = s[hi];
-            if (a > b) { s[lo] = b; s[hi] = a; }
-          }
-        }
-      } else {
-        const int lim = min(half, (n + 1) >> 1);
-        for (int i = threadIdx.x; i < lim; i += THREADS) {
-          const int lo = ((i & ~(j - 1)) << 1) | (i & (j - 1));
-          const int hi = lo | j;
-          if (hi < n) {
-            const uint64_t a = s[lo], b = s[hi];
-            if (a > b) { s[lo] = b; s[hi] = a; }
-          }
-        }
+// One CTA per tile, two launches over the same grid: a light variant (128 threads x 8 keys, 1024-key window) for
+// the common short lists and a heavy one (256 threads x 16 keys, 4096-key window, global radix fallback beyond
+// that); a CTA whose tile belongs to the other class exits at once.  Lists inside the window are sorted by the
+// shared-memory merge sort below (it replaced a bitonic network: 0.146 -> 0.135 ms on the benchmark frame).
+
+// ---- merge sort of one tile's keys in shared memory ------------------------------------------------
+// Thread t owns keys [t*VT, (t+1)*VT): it sorts them in registers (odd-even transposition network), then
+// log2(n/VT) merge passes follow; in each pass the thread finds, by a merge-path binary search on its output
+// diagonal, where its VT outputs start in the two sorted runs and merges them sequentially.  Work is
+// O(n log n) comparisons with n the real list length (only ceil(n/VT) threads take part, the tail is padded
+// with +inf to a multiple of VT) — about 2.5x fewer issued instructions per key than the bitonic network
+// (O(n log^2 n)) it replaces for the in-window lists, and independent of how the depths are distributed.
+// Keys are unique ((depth, id) with one instance per Gaussian and tile), so no stability rule is needed.
+// Returns the buffer that holds the sorted keys.
+template <int THREADS, int VT>
+__device__ __forceinline__ uint64_t* merge_sort_smem(uint64_t* a, uint64_t* b, const uint64_t* __restrict__ bucket, int n) {
+  const int t = threadIdx.x;
+  const int nchunks = (n + VT - 1) / VT;
+  const int n_pad = nchunks * VT;
+  if (t < nchunks) {
+    uint64_t k[VT];
+#pragma unroll
+    for (int i = 0; i < VT; i++) { const int idx = t * VT + i; k[i] = idx < n ? bucket[idx] : ~0ull; }
+#pragma unroll
+    for (int r = 0; r < VT; r++) {
+#pragma unroll
+      for (int i = (r & 1); i + 1 < VT; i += 2) {
+        const uint64_t lo = min(k[i], k[i + 1]), hi = max(k[i], k[i + 1]);
+        k[i] = lo; k[i + 1] = hi;
       }
-      // the next stage has stride j/2 (or k for the next round's mirror stage): it is warp-local iff that stride
-      // is <= 32, and this stage's writes came from the same warp iff j <= 32
-      if (j > 32 || (j == 1 && (k << 1) > 64 && k < n2)) __syncthreads();
-      else __syncwarp();
     }
+#pragma unroll
+    for (int i = 0; i < VT; i++) a[t * VT + i] = k[i];
   }
   __syncthreads();
+  uint64_t* src = a;
+  uint64_t* dst = b;
+  for (int L = VT; L < n_pad; L <<= 1) {
+    if (t < nchunks) {
+      const int out0 = t * VT;
+      const int pair0 = out0 & ~(2 * L - 1);                 // 2L is a power of two
+      const int lenA = min(L, n_pad - pair0);
+      const int lenB = min(L, max(0, n_pad - pair0 - L));
+      const uint64_t* A = src + pair0;
+      const uint64_t* B = src + pair0 + L;
+      const int diag = out0 - pair0;
+      int lo = max(0, diag - lenB), hi = min(diag, lenA);
+      while (lo < hi) {                                      // first a with A[a] > B[diag-1-a]
+        const int mid = (lo + hi) >> 1;
+        if (A[mid] <= B[diag - 1 - mid]) lo = mid + 1; else hi = mid;
+      }
+      int ai = lo, bi = diag - lo;
+      uint64_t ka = ai < lenA ? A[ai] : ~0ull, kb = bi < lenB ? B[bi] : ~0ull;
+#pragma unroll
+      for (int i = 0; i < VT; i++) {
+        const bool takeA = (bi >= lenB) || (ai < lenA && ka <= kb);
+        dst[out0 + i] = takeA ? ka : kb;
+        if (takeA) { ai++; ka = ai < lenA ? A[ai] : ~0ull; }
+        else { bi++; kb = bi < lenB ? B[bi] : ~0ull; }
+      }
+    }
+    __syncthreads();
+    uint64_t* tmp = src; src = dst; dst = tmp;
+  }
+  return src;
 }
 
 // stable LSD radix sort of n 64-bit keys, 8 bits per pass, one CTA of 256 threads, global ping-pong
@@ -221,15 +239,14 @@ tile_sort_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
   const uint2 rg = ranges[blockIdx.x];
   const int n = (int)(rg.y - rg.x);
   if (n <= MIN_N || (MIN_N == 0 && n > WINDOW)) return;   // other variant's tile (or empty)
-  __shared__ uint64_t s[WINDOW];
+  extern __shared__ __align__(16) unsigned char sort_smem[];
+  uint64_t* s = reinterpret_cast<uint64_t*>(sort_smem);        // [WINDOW]
+  uint64_t* s2 = s + WINDOW;                                    // [WINDOW]
   uint64_t* bucket = keys + rg.x;
   if (n <= WINDOW) {
-    int n2 = 2; while (n2 < n) n2 <<= 1;
-    for (int i = threadIdx.x; i < n; i += THREADS) s[i] = bucket[i];
-    __syncthreads();
-    bitonic_smem<THREADS>(s, n, n2);
+    const uint64_t* sorted = merge_sort_smem<THREADS, WINDOW / THREADS>(s, s2, bucket, n);
     for (int i = threadIdx.x; i < n; i += THREADS) {
-      const uint64_t k = s[i];
+      const uint64_t k = sorted[i];
       bucket[i] = k;
       point_list[rg.x + i] = (uint32_t)k;
     }
@@ -262,10 +279,16 @@ void sfgs_launch_scatter(const ImageLayout& im, const BinningLayout& b, unsigned
 }
 
 void sfgs_launch_tile_sort(const GeomLayout& g, const ImageLayout& im, const BinningLayout& b, cudaStream_t st) {
+  constexpr size_t smem_light = 2 * 1024 * sizeof(uint64_t), smem_heavy = 2 * 4096 * sizeof(uint64_t);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(tile_sort_kernel<256, 4096, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_heavy);
+    attr_set = true;
+  }
   SFGS_COUNT_LAUNCH();
-  tile_sort_kernel<128, 1024, 0><<<im.tiles, 128, 0, st>>>(im.ranges, im.hdr, b.keys, b.keys_tmp, b.point_list, g.rec,
-                                                           im.tiles_x, b.inst_mask);
+  tile_sort_kernel<128, 1024, 0><<<im.tiles, 128, smem_light, st>>>(im.ranges, im.hdr, b.keys, b.keys_tmp, b.point_list,
+                                                                     g.rec, im.tiles_x, b.inst_mask);
   SFGS_COUNT_LAUNCH();
-  tile_sort_kernel<256, 4096, 1024><<<im.tiles, 256, 0, st>>>(im.ranges, im.hdr, b.keys, b.keys_tmp, b.point_list,
-                                                              g.rec, im.tiles_x, b.inst_mask);
+  tile_sort_kernel<256, 4096, 1024><<<im.tiles, 256, smem_heavy, st>>>(im.ranges, im.hdr, b.keys, b.keys_tmp,
+                                                                        b.point_list, g.rec, im.tiles_x, b.inst_mask);
 }
