@@ -41,7 +41,7 @@
 extern "C" {
 #endif
 
-#define SFGS_VERSION 1
+#define SFGS_VERSION 2          /* 2: out_norm_raw / norm_raw, two-phase backward, activations, geometry-free scratch allocator */
 #define SFGS_TILE 16          /* BLOCK_X = BLOCK_Y = 16, RAST/cuda_rasterizer/config.h:15-17 */
 #define SFGS_MAX_EXTRA 34     /* MAX_EXTRA_DIMS, RAST/cuda_rasterizer/auxiliary.h:20 */
 

@@ -81,6 +81,8 @@ class BinningView(C.Structure):
 
 
 # every symbol include/sfgs.h declares
+ABI_VERSION = 2   # SFGS_VERSION of include/sfgs.h these struct mirrors were written for
+
 EXPORTS = [
     "sfgs_rasterize_forward", "sfgs_rasterize_backward", "sfgs_mark_visible",
     "sfgs_geom_bytes", "sfgs_image_bytes", "sfgs_binning_bytes",
@@ -132,6 +134,8 @@ def lib() -> C.CDLL:
     L.sfgs_activations_backward.restype = C.c_int
     L.sfgs_last_error.argtypes = []; L.sfgs_last_error.restype = C.c_char_p
     L.sfgs_version.argtypes = []; L.sfgs_version.restype = C.c_int
+    if L.sfgs_version() != ABI_VERSION:
+        raise ImportError(f"{LIB_PATH} has ABI v{L.sfgs_version()}, these bindings expect v{ABI_VERSION}: rebuild it")
     L.sfgs_launch_count.argtypes = []; L.sfgs_launch_count.restype = C.c_longlong
     L.sfgs_sizeof.argtypes = [C.c_int]; L.sfgs_sizeof.restype = C.c_size_t
     L.sfgs_sm_clock_probe.argtypes = [C.c_void_p, C.c_void_p]; L.sfgs_sm_clock_probe.restype = C.c_int
