@@ -201,7 +201,7 @@ def test_edge_cases(cuda_device):
 
 
 def test_long_tile_lists_use_both_sort_paths(cuda_device):
-    """> 1024 and > 4096 instances in one tile exercise the heavy bitonic window and the global radix fallback."""
+    """> 1024 and > 4096 instances in one tile exercise the heavy sort window and the global radix fallback."""
     if not ref_available():
         pytest.skip("oracle/_ref not built")
     from oracle import ref_cuda
@@ -337,6 +337,40 @@ def test_two_phase_backward_equals_single_call(cuda_device):
         assert got.shape == ref[k].shape
         tol = 1e-5 + 2e-4 * ref[k].abs().max().item()         # the sums themselves carry the reductions' order noise
         assert (got - ref[k]).abs().max().item() <= tol, k
+
+
+def test_4k_frame_many_tiles_and_debug_mode(cuda_device):
+    """3840x2160 = 32400 tiles: more than one pass of the single-CTA tile scan (8192 tiles per pass), ragged right
+    and bottom edges; checked against the CPU oracle.  Also runs the per-stage synchronising debug mode."""
+    from oracle import cpu_oracle as O
+    dev = cuda_device
+    scene = S.blob_scene(20_000, seed=17, spread=3.0, scale=0.05)
+    cam = S.simple_camera(3840, 2160, fov_deg=70.0, distance=6.0)
+    bg = np.array([0.2, 0.1, 0.0], np.float32)
+    d = Hh.to_torch(scene, cam, dev)
+    f = Hh.run_ours_forward(d, cam, 3, torch.from_numpy(bg).to(dev))
+    o = O.forward(scene.means3D, scene.scales, scene.rotations, scene.opacities, scene.shs, 3, cam.viewmatrix,
+                  cam.projmatrix, cam.campos, cam.width, cam.height, cam.tanfovx, cam.tanfovy, bg)
+    assert f["num_rendered"] == o["num_rendered"] > 0 and np.array_equal(f["radii"].cpu().numpy(), o["radii"])
+    it = Hh.our_internals(f, scene.P, cam.height, cam.width)
+    assert np.array_equal(it["ranges"].cpu().numpy().astype(np.uint32), o["ranges"])
+    assert np.array_equal(it["point_list"].cpu().numpy().astype(np.uint32), o["point_list"])
+    for k in ("color", "depth", "alpha"):   # CPU libm expf vs CUDA expf: isolated 1/255-threshold flips are possible
+        dlt = np.abs(f[k].cpu().numpy() - o[k])
+        assert np.quantile(dlt, 0.9999) <= 1e-5 * max(1.0, float(np.abs(o[k]).max())), k
+    # debug mode: every stage is followed by a synchronise + error check; results must not change
+    from sfgs import rasterizer as R
+    e = torch.empty(0, device=dev)
+    g = R.rasterize_gaussians(torch.from_numpy(bg).to(dev), d["means3D"], e, d["opacities"], d["scales"], d["rotations"],
+                              1.0, e, e, e, 0, d["viewmatrix"], d["projmatrix"], cam.tanfovx, cam.tanfovy, 0.1,
+                              cam.height, cam.width, d["shs"], 3, d["campos"], False, True)
+    assert g[0] == f["num_rendered"] and torch.equal(g[1], f["color"]) and torch.equal(g[4], f["alpha"])
+    cot = [torch.from_numpy(c).to(dev) for c in S.cotangents(cam.width, cam.height, seed=3)]
+    b0 = Hh.run_ours_backward(d, cam, 3, torch.from_numpy(bg).to(dev), f, cot)
+    b1 = Hh.run_ours_backward(d, cam, 3, torch.from_numpy(bg).to(dev), f, cot, debug=True)
+    for k in b0:
+        if b0[k].numel():
+            assert (b0[k] - b1[k]).abs().max().item() <= 1e-5 + 2e-4 * b0[k].abs().max().item(), k
 
 
 def test_mark_visible_matches_oracle(cuda_device):
