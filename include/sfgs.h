@@ -172,6 +172,14 @@ typedef struct sfgs_backward_args {
   int phase;
   float* acc;
   int gauss_begin, gauss_end;
+  /* optional, phase 1 only: the reduce-scatter FUSED into the blend adjoint (one node, NVLink / NVSwitch peer
+   * access).  acc_peers[r], r = 0..n_peers-1 (host array, n_peers <= 8), is rank r's [peer_slice,16] accumulator
+   * slice as a peer-mapped device pointer; Gaussian g is accumulated into acc_peers[g / peer_slice] +
+   * (g % peer_slice)*16 with system-scope vector reductions that travel over NVLink tile by tile while the kernel
+   * computes, so no separate collective follows.  The call clears nothing and `acc` is ignored: every rank clears
+   * its own slice and synchronises with its peers before and after the call (sfgs/multigpu.py). */
+  float* const* acc_peers;
+  int n_peers, peer_slice;
 } sfgs_backward_args;
 
 int sfgs_rasterize_backward(const sfgs_backward_args* a);

@@ -278,7 +278,11 @@ int sfgs_rasterize_backward(const sfgs_backward_args* a) {
     return fail(SFGS_E_BADARG, "backward: null output");
   if (do_gauss && a->M > 0 && a->shs && !a->dL_dsh) return fail(SFGS_E_BADARG, "backward: dL_dsh missing");
   if (a->ED > 0 && (!a->dL_dextra || !a->dL_dpix_extra || !a->extra_attrs)) return fail(SFGS_E_BADARG, "backward: extra attrs missing");
-  if (phase != 0 && !a->acc) return fail(SFGS_E_BADARG, "backward: phases 1 and 2 need the caller's acc buffer");
+  const bool peer = a->acc_peers != nullptr;
+  if (peer && (phase != 1 || a->n_peers < 1 || a->n_peers > 8 || a->peer_slice < 1 ||
+               (long long)a->n_peers * a->peer_slice < a->P))
+    return fail(SFGS_E_BADARG, "backward: acc_peers needs phase 1, 1..8 peers and n_peers*peer_slice >= P");
+  if (phase != 0 && !a->acc && !peer) return fail(SFGS_E_BADARG, "backward: phases 1 and 2 need the caller's acc buffer");
   if (phase == 0 && !a->acc && !a->scratch_alloc) return fail(SFGS_E_BADARG, "backward: null scratch allocator");
   if (a->acc && (reinterpret_cast<uintptr_t>(a->acc) & 15)) return fail(SFGS_E_BADARG, "backward: acc must be 16-byte aligned");
   if (a->rotations && (reinterpret_cast<uintptr_t>(a->rotations) & 15)) return fail(SFGS_E_BADARG, "backward: rotations must be 16-byte aligned");
@@ -300,7 +304,7 @@ int sfgs_rasterize_backward(const sfgs_backward_args* a) {
   const float focal_x = a->width / (2.0f * a->tan_fovx);
 
   float* acc = a->acc;
-  if (!acc) {
+  if (!acc && !peer) {
     const size_t abytes = (size_t)P * 16 * sizeof(float) + SFGS_ALIGN;
     char* aptr = a->scratch_alloc(a->scratch_user, abytes);
     if (!aptr) return fail(SFGS_E_ALLOC, "backward: scratch allocator returned NULL");
@@ -312,7 +316,8 @@ int sfgs_rasterize_backward(const sfgs_backward_args* a) {
     PROF_BEGIN(ST_BWD_ZERO);
     // one call: only rows of rasterized Gaussians are ever accumulated into or read; two-phase: the caller sums
     // whole buffers across ranks, so every row must be defined
-    if (phase == 0 && a->radii) sfgs_launch_acc_clear_visible(P, a->radii, acc, st);
+    if (peer) { /* the ranks clear their own slices and synchronise around this call */ }
+    else if (phase == 0 && a->radii) sfgs_launch_acc_clear_visible(P, a->radii, acc, st);
     else CU(cudaMemsetAsync(acc, 0, (size_t)P * 16 * sizeof(float), st));
     if (a->ED > 0) CU(cudaMemsetAsync(a->dL_dextra, 0, (size_t)P * a->ED * sizeof(float), st));
     PROF_END();

@@ -52,12 +52,26 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::); }
 
+// PEER: the target may be another GPU's memory reached over NVLink and every GPU of the node adds into it, so the
+// reduction must be system-scope; otherwise the default (device) scope
+template <bool PEER>
 __device__ __forceinline__ void red_add_v4(float* addr, float4 v) {
-  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
-               : "memory");
+  if (PEER)
+    asm volatile("red.relaxed.sys.global.add.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z),
+                 "f"(v.w)
+                 : "memory");
+  else
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                 : "memory");
 }
 
-template <bool HAS_EXTRA>
+// peer-mapped accumulator slices of the ranks of one node (sfgs_backward_args.acc_peers)
+struct PeerTable {
+  float* p[8];
+  int per;      // Gaussians per slice
+};
+
+template <bool HAS_EXTRA, bool PEER>
 __global__ void __launch_bounds__(BWD_THREADS, 3)
 render_bwd_kernel(const uint2* __restrict__ ranges, const char* __restrict__ binning_base,
                   const uint32_t* __restrict__ hdr, int W, int H, int ED, int band0,
@@ -66,7 +80,8 @@ render_bwd_kernel(const uint2* __restrict__ ranges, const char* __restrict__ bin
                   const uint32_t* __restrict__ n_contrib, const float* __restrict__ dL_dpixels,
                   const float* __restrict__ dL_dpixel_depths, const float* __restrict__ dL_dpixel_norms,
                   const float* __restrict__ dL_dpixel_alphas, const float* __restrict__ dL_dpixel_extras,
-                  const float* __restrict__ norm_raw, float* __restrict__ acc /* [P,16] zero-initialised */, float* __restrict__ dL_dextras) {
+                  const float* __restrict__ norm_raw, float* __restrict__ acc /* [P,16] zero-initialised */, float* __restrict__ dL_dextras,
+                  const PeerTable peers) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   BwdSmem& S = *reinterpret_cast<BwdSmem*>(smem_raw);
 
@@ -211,14 +226,20 @@ render_bwd_kernel(const uint2* __restrict__ ranges, const char* __restrict__ bin
 #undef XH
     if (have) {
       const float o = rb.y;
-      float* dst = acc + (size_t)gid * 16;
-      if (chalf == 0) {
-        red_add_v4(dst, make_float4(s0, s1, s2, s3));
-        red_add_v4(dst + 4, make_float4(s4, s5, s6, -ddelx_dx * o * fmaf(ra.z, shx, ra.w * shy)));
+      float* dst;
+      if (PEER) {   // the sums of Gaussian gid live on rank gid / per: the reduction itself is the reduce-scatter
+        const uint32_t r = gid / (uint32_t)peers.per;
+        dst = peers.p[r] + (size_t)(gid - r * (uint32_t)peers.per) * 16;
       } else {
-        red_add_v4(dst + 8, make_float4(-ddely_dy * o * fmaf(rb.x, shy, ra.w * shx), fabsf(o) * sab, -0.5f * o * shxx,
-                                        -0.5f * o * shxy));
-        red_add_v4(dst + 12, make_float4(-0.5f * o * shyy, sh, 0.f, 0.f));
+        dst = acc + (size_t)gid * 16;
+      }
+      if (chalf == 0) {
+        red_add_v4<PEER>(dst, make_float4(s0, s1, s2, s3));
+        red_add_v4<PEER>(dst + 4, make_float4(s4, s5, s6, -ddelx_dx * o * fmaf(ra.z, shx, ra.w * shy)));
+      } else {
+        red_add_v4<PEER>(dst + 8, make_float4(-ddely_dy * o * fmaf(rb.x, shy, ra.w * shx), fabsf(o) * sab,
+                                              -0.5f * o * shxx, -0.5f * o * shxy));
+        red_add_v4<PEER>(dst + 12, make_float4(-0.5f * o * shyy, sh, 0.f, 0.f));
       }
     }
     __syncwarp();
@@ -312,19 +333,27 @@ void sfgs_launch_render_bwd(const sfgs_backward_args* a, const GeomLayout& g, co
   const size_t smem = sizeof(BwdSmem);
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(render_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaFuncSetAttribute(render_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(render_bwd_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(render_bwd_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(render_bwd_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(render_bwd_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     attr_set = true;
   }
+  PeerTable pt = {};
+  const bool peer = a->acc_peers != nullptr && a->n_peers > 0;
+  if (peer) {
+    for (int r = 0; r < a->n_peers && r < 8; r++) pt.p[r] = a->acc_peers[r];
+    pt.per = a->peer_slice;
+  }
+  const bool ex = a->ED > 0;
   SFGS_COUNT_LAUNCH();
-  if (a->ED > 0)
-    render_bwd_kernel<true><<<grid, BWD_THREADS, smem, st>>>(
-        im.ranges, (const char*)b.point_list, im.hdr, a->width, a->height, a->ED, band0, a->background, g.rec,
-        a->extra_attrs, a->accum_alphas, im.n_contrib, a->dL_dpix, a->dL_dpix_depth, a->dL_dpix_norm,
-        a->dL_dpix_alpha, a->dL_dpix_extra, a->norm_raw, acc, a->dL_dextra);
-  else
-    render_bwd_kernel<false><<<grid, BWD_THREADS, smem, st>>>(
-        im.ranges, (const char*)b.point_list, im.hdr, a->width, a->height, 0, band0, a->background, g.rec, nullptr,
-        a->accum_alphas, im.n_contrib, a->dL_dpix, a->dL_dpix_depth, a->dL_dpix_norm, a->dL_dpix_alpha, nullptr,
-        a->norm_raw, acc, nullptr);
+#define RB_ARGS                                                                                                        \
+  im.ranges, (const char*)b.point_list, im.hdr, a->width, a->height, (ex ? a->ED : 0), band0, a->background, g.rec,    \
+      (ex ? a->extra_attrs : nullptr), a->accum_alphas, im.n_contrib, a->dL_dpix, a->dL_dpix_depth, a->dL_dpix_norm,   \
+      a->dL_dpix_alpha, (ex ? a->dL_dpix_extra : nullptr), a->norm_raw, acc, (ex ? a->dL_dextra : nullptr), pt
+  if (ex && peer) render_bwd_kernel<true, true><<<grid, BWD_THREADS, smem, st>>>(RB_ARGS);
+  else if (ex) render_bwd_kernel<true, false><<<grid, BWD_THREADS, smem, st>>>(RB_ARGS);
+  else if (peer) render_bwd_kernel<false, true><<<grid, BWD_THREADS, smem, st>>>(RB_ARGS);
+  else render_bwd_kernel<false, false><<<grid, BWD_THREADS, smem, st>>>(RB_ARGS);
+#undef RB_ARGS
 }

@@ -22,6 +22,8 @@ world-size-2 gloo tests on CPU tensors; on B200s the backend is NCCL over NVLink
 """
 from __future__ import annotations
 
+import os
+import sys
 from typing import List, Sequence
 
 import torch
@@ -175,7 +177,7 @@ def bench_tilerows(args, rank, world, dev, steps, warmup, metric):
                                               cot[2], cot[3], e, d["shs"], 3, d["campos"], f[7], f[0], f[8], f[9], f[4],
                                               False, tile_rows=band, **kw)
 
-    def step():
+    def step_nccl():
         f = fwd(band)
         planes = torch.cat([f[1], f[2], f[4], f[3]], 0)            # colour, depth, alpha, normal: 8 planes
         full = gather_bands(planes, cuts, H)
@@ -184,6 +186,49 @@ def bench_tilerows(args, rank, world, dev, steps, warmup, metric):
         dist.reduce_scatter_tensor(mine, acc_buf, op=dist.ReduceOp.SUM)
         g = bwd(f, phase=2, acc=mine, gauss_range=(sl[rank], sl[rank + 1]))   # finish this rank's slice only
         return full, g
+
+    # Fused alternative: every rank's accumulator slice is symmetric (peer-mapped) memory and the blend adjoint's
+    # vector reductions go straight to the owning rank over NVLink — the reduce-scatter happens inside the kernel,
+    # tile by tile, and no collective follows it.  Falls back to the NCCL path when peer mapping is unavailable.
+    collective, step = "nccl reduce_scatter of the [P,16] blend-adjoint sums", step_nccl
+    if os.environ.get("SFGS_PEER_REDUCE", "1") != "0":
+        try:
+            import torch.distributed._symmetric_memory as symm
+            acc_sym = symm.empty((per * 16,), dtype=torch.float32, device=dev)
+            hdl = symm.rendezvous(acc_sym, dist.group.WORLD)
+            peers = [int(p) for p in hdl.buffer_ptrs]
+
+            def step_peer():
+                f = fwd(band)
+                planes = torch.cat([f[1], f[2], f[4], f[3]], 0)
+                full = gather_bands(planes, cuts, H)
+                acc_sym.zero_()
+                hdl.barrier(channel=0)                              # every slice is clear before anyone adds
+                bwd(f, phase=1, acc_peers=peers, peer_slice=per)    # reductions land on the owners' slices
+                hdl.barrier(channel=1)                              # every rank's kernel has completed
+                g = bwd(f, phase=2, acc=acc_sym.view(per, 16), gauss_range=(sl[rank], sl[rank + 1]))
+                return full, g
+
+            # agreement with the NCCL path on this rank's slice, before it is trusted
+            _, g_ref = step_nccl()
+            _, g_new = step_peer()
+            torch.cuda.synchronize(dev)
+            worst = 0.0
+            for a_, b_ in zip(g_ref, g_new):
+                if a_.numel():
+                    x, y = a_[sl[rank]:sl[rank + 1]], b_[sl[rank]:sl[rank + 1]]
+                    worst = max(worst, float(((x - y).abs().max() / (y.abs().max() + 1e-12)).item()))
+            ok = torch.tensor([1.0 if worst <= 1e-3 else 0.0], device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if ok.item() == 1.0:
+                collective, step = ("reduce-scatter fused into the blend adjoint: system-scope vector reductions to "
+                                    f"peer-mapped slices over NVLink (max rel. deviation from the NCCL path {worst:.1e})"), step_peer
+            elif rank == 0:
+                print(f"[tilerows] peer path disagrees with the NCCL path (rel {worst:.2e}); using NCCL", file=sys.stderr)
+        except Exception as exc:  # noqa: BLE001
+            flag = torch.tensor([0.0], device=dev)
+            if rank == 0:
+                print(f"[tilerows] symmetric memory unavailable ({type(exc).__name__}: {exc}); using NCCL", file=sys.stderr)
 
     for _ in range(warmup):
         step()
@@ -206,8 +251,7 @@ def bench_tilerows(args, rank, world, dev, steps, warmup, metric):
                           "data": "synthetic",
                           "config": {"workload": f"one 1920x1080 frame of the {scene.P}-Gaussian scene sharded by tile rows",
                                      "P": scene.P,
-                                     "parallelism": f"tilerows x{world}: image all_gather + reduce_scatter of the "
-                                                    "[P,16] blend-adjoint sums (NCCL); each rank finishes the "
-                                                    "gradients of P/N Gaussians",
+                                     "parallelism": f"tilerows x{world}: image all_gather (NCCL) + {collective}; each rank "
+                                                    "finishes the gradients of P/N Gaussians",
                                      "cuts": cuts, "l2": "not flushed (collectives in the loop)"}}))
     dist.destroy_process_group()

@@ -65,6 +65,7 @@ class BackwardArgs(C.Structure):
         ("tile_row_begin", C.c_int), ("tile_row_end", C.c_int),
         ("norm_raw", c_float_p),
         ("phase", C.c_int), ("acc", c_float_p), ("gauss_begin", C.c_int), ("gauss_end", C.c_int),
+        ("acc_peers", C.POINTER(C.c_void_p)), ("n_peers", C.c_int), ("peer_slice", C.c_int),
     ]
 
 

@@ -128,7 +128,7 @@ def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rot
                                  kernel_size, dL_dout_color, dL_dout_depth, dL_dout_norm, dL_dout_alpha,
                                  dL_dout_extra, sh, degree, campos, geomBuffer, R, binningBuffer, imageBuffer,
                                  out_alpha, debug, tile_rows=None, norm_raw=None, phase=0, acc=None,
-                                 gauss_range=None):
+                                 gauss_range=None, acc_peers=None, peer_slice=0):
     """Same positional signature and return tuple as the reference's `_C.rasterize_gaussians_backward`.  With
     `norm_raw` (the extra tensor a `fuse_normalize=True` forward returned) `dL_dout_norm` is taken w.r.t. the unit
     normal map and the adjoint of F.normalize is applied inside the blend-adjoint kernel.
@@ -165,7 +165,15 @@ def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rot
         keep = []
         a = N.BackwardArgs()
         a.phase = int(phase)
-        if phase == 1 and acc is None:
+        if acc_peers is not None:
+            # phase 1 with the reduce-scatter fused into the kernel: peer-mapped slice pointers, nothing allocated here
+            if phase != 1:
+                raise ValueError("acc_peers is a phase-1 option")
+            peer_arr = (C.c_void_p * len(acc_peers))(*[int(p) for p in acc_peers])
+            keep.append(peer_arr)                      # must outlive the call
+            a.acc_peers = C.cast(peer_arr, C.POINTER(C.c_void_p))
+            a.n_peers, a.peer_slice = len(acc_peers), int(peer_slice)
+        elif phase == 1 and acc is None:
             acc = torch.empty((P, 16), **fopt)
         if acc is not None:
             a.acc = _ptr(acc, keep)
@@ -217,7 +225,7 @@ def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rot
             a.tile_row_begin, a.tile_row_end = int(tile_rows[0]), int(tile_rows[1])
         N.check(L.sfgs_rasterize_backward(C.byref(a)), "sfgs_rasterize_backward")
     if phase == 1:
-        return acc
+        return acc      # None when the sums went straight to the peers' slices
     return (outs["means2D"], outs["colors"], outs["opacity"], outs["means3D"], outs["cov3D"], outs["norm3D"],
             dL_dsh, outs["scales"], outs["rot"], dL_dextra)
 

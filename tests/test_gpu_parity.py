@@ -327,6 +327,16 @@ def test_two_phase_backward_equals_single_call(cuda_device):
     ref = Hh.run_ours_backward(d, cam, 3, bg, f, cot)
     acc = Hh.run_ours_backward(d, cam, 3, bg, f, cot, phase=1)
     assert acc.shape == (scene.P, 16)
+    # the fused reduce-scatter variant with a single "peer" (this GPU): same sums through the system-scope path
+    acc_p = torch.zeros((scene.P, 16), device=dev)
+    assert Hh.run_ours_backward(d, cam, 3, bg, f, cot, phase=1, acc_peers=[acc_p.data_ptr()], peer_slice=scene.P) is None
+    assert (acc_p - acc).abs().max().item() <= 1e-5 + 2e-4 * acc.abs().max().item()
+    # ... and with two "peers" that are the two halves of one buffer
+    half = (scene.P + 1) // 2
+    acc_q = torch.zeros((2 * half, 16), device=dev)
+    Hh.run_ours_backward(d, cam, 3, bg, f, cot, phase=1, acc_peers=[acc_q.data_ptr(), acc_q[half:].data_ptr()],
+                         peer_slice=half)
+    assert (acc_q[:scene.P] - acc).abs().max().item() <= 1e-5 + 2e-4 * acc.abs().max().item()
     cut = 2173                                                   # deliberately not a multiple of the block span
     parts = [Hh.run_ours_backward(d, cam, 3, bg, f, cot, phase=2, acc=acc[a:b].clone(), gauss_range=(a, b))
              for a, b in ((0, cut), (cut, scene.P))]
