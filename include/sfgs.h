@@ -104,6 +104,13 @@ typedef struct sfgs_forward_args {
    * RAST/diff_gauss/__init__.py:48): when non-NULL, out_norm receives F.normalize(blend, p=2, dim=0, eps=1e-12)
    * and the un-normalised blend is stored here ([3,H,W]) for the backward. */
   float* out_norm_raw;
+  /* optional: the image all-gather of the tile-row sharded multi-GPU mode fused into the blend kernel.
+   * out_peers[r], r = 0..n_out_peers-1 (host array, <= 8), is rank r's [8,H,W] frame block (colour 3, depth 1,
+   * alpha 1, normal 3 planes, in this order) as a peer-mapped device pointer; the pixels of this rank's band are
+   * stored into every block (NVLink stores), so after a barrier every rank holds the whole frame.  out_color /
+   * out_depth / out_alpha / out_norm are then ignored. */
+  float* const* out_peers;
+  int n_out_peers;
 } sfgs_forward_args;
 
 /* Returns num_rendered (>= 0) or a negative SFGS_E_* code. */

@@ -171,7 +171,9 @@ int sfgs_rasterize_forward(const sfgs_forward_args* a) {
   if (a->P < 0 || a->width <= 0 || a->height <= 0) return fail(SFGS_E_BADARG, "forward: bad sizes");
   if (a->ED < 0 || a->ED > SFGS_MAX_EXTRA) return fail(SFGS_E_BADARG, "forward: ED out of range");
   if (a->tile_row_begin < 0 || a->tile_row_end < a->tile_row_begin) return fail(SFGS_E_BADARG, "forward: bad tile-row band");
-  if (!a->out_color || !a->out_depth || !a->out_norm || !a->out_alpha || (a->P > 0 && !a->radii))
+  const bool peer_out = a->out_peers != nullptr && a->n_out_peers > 0;
+  if (peer_out && a->n_out_peers > 8) return fail(SFGS_E_BADARG, "forward: at most 8 out_peers");
+  if ((!peer_out && (!a->out_color || !a->out_depth || !a->out_norm || !a->out_alpha)) || (a->P > 0 && !a->radii))
     return fail(SFGS_E_BADARG, "forward: null output");
   if (!a->geom_alloc || !a->binning_alloc || !a->image_alloc) return fail(SFGS_E_BADARG, "forward: null allocator");
   if (a->P > 0) {

@@ -30,6 +30,12 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
+// peer-mapped [8,H,W] frame blocks of the ranks of one node (sfgs_forward_args.out_peers); n == 0: local outputs
+struct OutPeers {
+  float* p[8];
+  int n;
+};
+
 template <bool HAS_EXTRA>
 __global__ void __launch_bounds__(FWD_THREADS)
 render_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list,
@@ -38,7 +44,8 @@ render_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
                   const float* __restrict__ rec, const float* __restrict__ extras,
                   const float* __restrict__ bg_color, float* __restrict__ out_color,
                   float* __restrict__ out_depth, float* __restrict__ out_norm, float* __restrict__ out_norm_raw,
-                  float* __restrict__ out_alpha, float* __restrict__ out_extra, uint32_t* __restrict__ n_contrib) {
+                  float* __restrict__ out_alpha, float* __restrict__ out_extra, uint32_t* __restrict__ n_contrib,
+                  const OutPeers peers) {
   if (hdr[HDR_OVERFLOW]) return;
   __shared__ __align__(16) float4 s_rec[FWD_STAGES][FWD_BATCH][4];   // 32 KB
   __shared__ uint32_t s_id[FWD_STAGES][FWD_BATCH];
@@ -136,12 +143,8 @@ render_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
 
   if (inside) {
     const size_t HW = (size_t)H * W;
-    out_alpha[pix_id] = 1 - T;
     n_contrib[pix_id] = last_contributor;
-    out_color[0 * HW + pix_id] = C0 + T * bg_color[0];
-    out_color[1 * HW + pix_id] = C1 + T * bg_color[1];
-    out_color[2 * HW + pix_id] = C2 + T * bg_color[2];
-    out_depth[pix_id] = Dp;
+    const float c0 = C0 + T * bg_color[0], c1 = C1 + T * bg_color[1], c2 = C2 + T * bg_color[2];
     if (out_norm_raw != nullptr) {
       // fused post-op: F.normalize(norm, p=2, dim=0, eps=1e-12) (RAST/diff_gauss/__init__.py:48); the raw blend is
       // kept for the adjoint
@@ -151,9 +154,25 @@ render_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
       const float d = fmaxf(sqrtf(N0 * N0 + N1 * N1 + N2 * N2), 1e-12f);
       N0 = N0 / d; N1 = N1 / d; N2 = N2 / d;
     }
-    out_norm[0 * HW + pix_id] = N0;
-    out_norm[1 * HW + pix_id] = N1;
-    out_norm[2 * HW + pix_id] = N2;
+    if (peers.n > 0) {
+      // the all-gather of the band: this pixel goes to every rank's frame (plane order colour, depth, alpha, normal)
+      for (int r = 0; r < peers.n; r++) {
+        float* f = peers.p[r];
+        f[0 * HW + pix_id] = c0; f[1 * HW + pix_id] = c1; f[2 * HW + pix_id] = c2;
+        f[3 * HW + pix_id] = Dp;
+        f[4 * HW + pix_id] = 1 - T;
+        f[5 * HW + pix_id] = N0; f[6 * HW + pix_id] = N1; f[7 * HW + pix_id] = N2;
+      }
+    } else {
+      out_alpha[pix_id] = 1 - T;
+      out_color[0 * HW + pix_id] = c0;
+      out_color[1 * HW + pix_id] = c1;
+      out_color[2 * HW + pix_id] = c2;
+      out_depth[pix_id] = Dp;
+      out_norm[0 * HW + pix_id] = N0;
+      out_norm[1 * HW + pix_id] = N1;
+      out_norm[2 * HW + pix_id] = N2;
+    }
     if (HAS_EXTRA)
       for (int ch = 0; ch < ED; ch++) out_extra[ch * HW + pix_id] = E[ch];
   }
@@ -167,15 +186,18 @@ void sfgs_launch_render_fwd(const sfgs_forward_args* a, const GeomLayout& g, con
   const int band1 = a->tile_row_end > a->tile_row_begin ? (a->tile_row_end < im.tiles_y ? a->tile_row_end : im.tiles_y) : im.tiles_y;
   if (band1 <= band0) return;
   dim3 grid(im.tiles_x, band1 - band0, 1);
+  OutPeers op = {};
+  if (a->out_peers != nullptr && a->n_out_peers > 0)
+    for (op.n = 0; op.n < a->n_out_peers && op.n < 8; op.n++) op.p[op.n] = a->out_peers[op.n];
   SFGS_COUNT_LAUNCH();
   if (a->ED > 0)
     render_fwd_kernel<true><<<grid, FWD_THREADS, 0, st>>>(im.ranges, b.point_list, b.inst_mask, im.hdr, a->width, a->height, a->ED, band0,
                                                          g.rec, a->extra_attrs, a->background, a->out_color,
                                                          a->out_depth, a->out_norm, a->out_norm_raw, a->out_alpha,
-                                                         a->out_extra, im.n_contrib);
+                                                         a->out_extra, im.n_contrib, op);
   else
     render_fwd_kernel<false><<<grid, FWD_THREADS, 0, st>>>(im.ranges, b.point_list, b.inst_mask, im.hdr, a->width, a->height, 0, band0,
                                                           g.rec, nullptr, a->background, a->out_color, a->out_depth,
                                                           a->out_norm, a->out_norm_raw, a->out_alpha, nullptr,
-                                                          im.n_contrib);
+                                                          im.n_contrib, op);
 }

@@ -191,6 +191,7 @@ def bench_tilerows(args, rank, world, dev, steps, warmup, metric):
     # vector reductions go straight to the owning rank over NVLink — the reduce-scatter happens inside the kernel,
     # tile by tile, and no collective follows it.  Falls back to the NCCL path when peer mapping is unavailable.
     collective, step = "nccl reduce_scatter of the [P,16] blend-adjoint sums", step_nccl
+    gather = "image all_gather (NCCL)"
     if os.environ.get("SFGS_PEER_REDUCE", "1") != "0":
         try:
             import torch.distributed._symmetric_memory as symm
@@ -198,10 +199,20 @@ def bench_tilerows(args, rank, world, dev, steps, warmup, metric):
             hdl = symm.rendezvous(acc_sym, dist.group.WORLD)
             peers = [int(p) for p in hdl.buffer_ptrs]
 
+            # forward: the frame block of every rank is symmetric memory too; the blend kernel stores its band into
+            # all of them (the image all-gather, fused), and one barrier publishes the frame
+            frame_sym = symm.empty((8 * H * W,), dtype=torch.float32, device=dev)
+            fh = symm.rendezvous(frame_sym, dist.group.WORLD)
+            frame_peers = [int(p) for p in fh.buffer_ptrs]
+
             def step_peer():
-                f = fwd(band)
-                planes = torch.cat([f[1], f[2], f[4], f[3]], 0)
-                full = gather_bands(planes, cuts, H)
+                fh.barrier(channel=0)                               # nobody still reads the previous frame
+                f = R.rasterize_gaussians(d["bg"], d["means3D"], e, d["opacities"], d["scales"], d["rotations"], 1.0,
+                                          e, e, e, 0, d["view"], d["proj"], cam.tanfovx, cam.tanfovy, 0.1, H, W,
+                                          d["shs"], 3, d["campos"], False, False, tile_rows=band,
+                                          out_planes=frame_sym, out_peers=frame_peers)
+                fh.barrier(channel=1)                               # every band has landed everywhere
+                full = frame_sym.view(8, H, W)
                 acc_sym.zero_()
                 hdl.barrier(channel=0)                              # every slice is clear before anyone adds
                 bwd(f, phase=1, acc_peers=peers, peer_slice=per)    # reductions land on the owners' slices
@@ -210,10 +221,10 @@ def bench_tilerows(args, rank, world, dev, steps, warmup, metric):
                 return full, g
 
             # agreement with the NCCL path on this rank's slice, before it is trusted
-            _, g_ref = step_nccl()
-            _, g_new = step_peer()
+            full_ref, g_ref = step_nccl()
+            full_new, g_new = step_peer()
             torch.cuda.synchronize(dev)
-            worst = 0.0
+            worst = 0.0 if torch.equal(full_ref, full_new) else float("inf")   # the frames must agree bit for bit
             for a_, b_ in zip(g_ref, g_new):
                 if a_.numel():
                     x, y = a_[sl[rank]:sl[rank + 1]], b_[sl[rank]:sl[rank + 1]]
@@ -221,6 +232,7 @@ def bench_tilerows(args, rank, world, dev, steps, warmup, metric):
             ok = torch.tensor([1.0 if worst <= 1e-3 else 0.0], device=dev)
             dist.all_reduce(ok, op=dist.ReduceOp.MIN)
             if ok.item() == 1.0:
+                gather = "image all-gather fused into the blend kernel (peer stores)"
                 collective, step = ("reduce-scatter fused into the blend adjoint: system-scope vector reductions to "
                                     f"peer-mapped slices over NVLink (max rel. deviation from the NCCL path {worst:.1e})"), step_peer
             elif rank == 0:
@@ -251,7 +263,7 @@ def bench_tilerows(args, rank, world, dev, steps, warmup, metric):
                           "data": "synthetic",
                           "config": {"workload": f"one 1920x1080 frame of the {scene.P}-Gaussian scene sharded by tile rows",
                                      "P": scene.P,
-                                     "parallelism": f"tilerows x{world}: image all_gather (NCCL) + {collective}; each rank "
+                                     "parallelism": f"tilerows x{world}: {gather} + {collective}; each rank "
                                                     "finishes the gradients of P/N Gaussians",
                                      "cuts": cuts, "l2": "not flushed (collectives in the loop)"}}))
     dist.destroy_process_group()

@@ -38,6 +38,7 @@ class ForwardArgs(C.Structure):
         ("debug", C.c_int), ("stream", C.c_void_p), ("capacity_hint", C.c_longlong),
         ("tile_row_begin", C.c_int), ("tile_row_end", C.c_int),
         ("out_norm_raw", c_float_p),
+        ("out_peers", C.POINTER(C.c_void_p)), ("n_out_peers", C.c_int),
     ]
 
 

@@ -55,7 +55,8 @@ class _Arena:
 def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations, scale_modifier,
                         cov3Ds_precomp, norm3Ds_precomp, extra_attrs, attr_degree, viewmatrix, projmatrix,
                         tan_fovx, tan_fovy, kernel_size, image_height, image_width, sh, degree, campos,
-                        prefiltered, debug, capacity_hint=0, tile_rows=None, fuse_normalize=False):
+                        prefiltered, debug, capacity_hint=0, tile_rows=None, fuse_normalize=False, out_planes=None,
+                        out_peers=None):
     """Same positional signature and return tuple as the reference's `_C.rasterize_gaussians`.  With
     `fuse_normalize=True` the returned normal map is already F.normalize(., dim=0) (the reference's torch post-op,
     diff_gauss/__init__.py:48) and the un-normalised blend is appended to the tuple for the backward."""
@@ -78,9 +79,15 @@ def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations,
 
     with torch.cuda.device(dev):
         # one allocation for the 8 image planes: colour(3) depth(1) alpha(1) normal(3)
-        planes = torch.empty((11 if fuse_normalize else 8, H, W), **fopt)
+        # multi-GPU tile-row mode: `out_planes` is this rank's symmetric [8,H,W] frame block and `out_peers` the
+        # peer-mapped pointers of every rank's block; the blend kernel then stores the band into all of them
+        if out_planes is not None:
+            planes = out_planes.view(8, H, W)
+            norm_raw = torch.empty((3, H, W), **fopt) if fuse_normalize else None
+        else:
+            planes = torch.empty((11 if fuse_normalize else 8, H, W), **fopt)
+            norm_raw = planes[8:11] if fuse_normalize else None
         out_color, out_depth, out_alpha, out_norm = planes[0:3], planes[3:4], planes[4:5], planes[5:8]
-        norm_raw = planes[8:11] if fuse_normalize else None
         radii = torch.empty((P,), dtype=torch.int32, device=dev)
         out_extra = torch.empty((F, H, W), **fopt) if F > 0 else torch.empty(0, **fopt)
 
@@ -111,6 +118,11 @@ def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations,
         a.out_norm, a.out_alpha = out_norm.data_ptr(), out_alpha.data_ptr()
         a.out_extra = out_extra.data_ptr() if F > 0 else None
         a.out_norm_raw = norm_raw.data_ptr() if fuse_normalize else None
+        if out_peers is not None:
+            peer_arr = (C.c_void_p * len(out_peers))(*[int(p) for p in out_peers])
+            keep.append(peer_arr)
+            a.out_peers = C.cast(peer_arr, C.POINTER(C.c_void_p))
+            a.n_out_peers = len(out_peers)
         a.radii = radii.data_ptr()
         a.debug = int(bool(debug))
         a.stream = torch.cuda.current_stream(dev).cuda_stream
