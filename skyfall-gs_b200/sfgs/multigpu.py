@@ -238,7 +238,6 @@ def bench_tilerows(args, rank, world, dev, steps, warmup, metric):
             elif rank == 0:
                 print(f"[tilerows] peer path disagrees with the NCCL path (rel {worst:.2e}); using NCCL", file=sys.stderr)
         except Exception as exc:  # noqa: BLE001
-            flag = torch.tensor([0.0], device=dev)
             if rank == 0:
                 print(f"[tilerows] symmetric memory unavailable ({type(exc).__name__}: {exc}); using NCCL", file=sys.stderr)
 
