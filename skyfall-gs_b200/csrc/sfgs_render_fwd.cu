@@ -30,6 +30,41 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
+// ---- optional TMA staging: one bulk copy (cp.async.bulk, SASS UBLKCP) per 64-byte blend record, completion by
+// mbarrier (each staging warp posts its byte count with one arrive.expect_tx; the phase completes when all eight
+// warps have arrived and all announced bytes have landed).  Measured on B200: parity-green but 5 % SLOWER than the
+// cp.async path (0.322 vs 0.305 ms): UBLKCP is a uniform-datapath instruction, so a warp whose 32 lanes gather 32
+// scattered records issues 32 serialised bulk copies where LDGSTS issues 4 vector instructions.  TMA pays for
+// tiles, not for 64-byte gathers — the default stays cp.async; build with -DSFGS_TMA_STAGING=1 to reproduce.
+#ifndef SFGS_TMA_STAGING
+#define SFGS_TMA_STAGING 0
+#endif
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(a), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, unsigned bytes) {
+  const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(a), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+  const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(a) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  unsigned ok;
+  do {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                 : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void tma_load_64(void* smem, const void* gmem, unsigned long long* bar) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem), b = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], 64, [%2];\n"
+               ::"r"(d), "l"(gmem), "r"(b) : "memory");
+}
+
 // peer-mapped [8,H,W] frame blocks of the ranks of one node (sfgs_forward_args.out_peers); n == 0: local outputs
 struct OutPeers {
   float* p[8];
@@ -77,6 +112,17 @@ render_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
   }
   bool done = !inside;
 
+#if SFGS_TMA_STAGING
+  __shared__ __align__(8) unsigned long long s_mbar[FWD_STAGES];
+  if (tid == 0) {
+    mbar_init(&s_mbar[0], FWD_THREADS / 32);
+    mbar_init(&s_mbar[1], FWD_THREADS / 32);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+  }
+  __syncthreads();
+#endif
+
   // stage loader: thread t copies record t of the batch (skipped when no block of the tile can be reached) and
   // the warp publishes, per pixel block, the ballot of "this record reaches the block".
   auto issue = [&](int batch, int stage) {
@@ -87,12 +133,26 @@ render_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
       if (m) {
         const uint32_t id = point_list[range.x + e];
         const float* src = rec + (size_t)id * REC_FLOATS;
+#if SFGS_TMA_STAGING
+        tma_load_64(&s_rec[stage][tid][0], src, &s_mbar[stage]);
+#else
 #pragma unroll
         for (int q = 0; q < 4; q++) cp_async16(&s_rec[stage][tid][q], src + q * 4);
+#endif
         if (HAS_EXTRA) s_id[stage][tid] = id;
       }
     }
+#if SFGS_TMA_STAGING
+    {
+      const unsigned nrec = __popc(__ballot_sync(0xffffffffu, m != 0));
+      if (lane == 0) {
+        if (nrec) mbar_arrive_expect_tx(&s_mbar[stage], nrec * 64u);
+        else mbar_arrive(&s_mbar[stage]);
+      }
+    }
+#else
     cp_async_commit();
+#endif
 #pragma unroll
     for (int blk = 0; blk < FWD_THREADS / 32; blk++) {
       const unsigned word = __ballot_sync(0xffffffffu, (m >> blk) & 1u);
@@ -103,7 +163,11 @@ render_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
   if (nbatches > 0) issue(0, 0);
   for (int b = 0; b < nbatches; b++) {
     const int stage = b & 1;
+#if SFGS_TMA_STAGING
+    mbar_wait(&s_mbar[stage], (unsigned)(b >> 1) & 1u);
+#else
     cp_async_wait<0>();
+#endif
     // barrier: stage `b` visible to all, stage `b^1` no longer read by anyone
     const int num_done = __syncthreads_count(done);
     if (num_done == FWD_THREADS) break;
