@@ -481,7 +481,7 @@ def main():
         out["impl"] = "reference"
         out["reference_kind"] = "unmodified reference CUDA rasterizer (oracle/_ref), same GPU, same inputs"
         out["e2e"]["note"] = "same host<->device copies as the product arm"
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:   # the CPU port is timed on rank 0 of the single-GPU run only
         out["cpu_baseline"] = cpu_baseline(scene, cam)
     print(json.dumps(out))
     if world > 1:
