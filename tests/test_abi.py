@@ -60,6 +60,47 @@ def test_error_paths_without_gpu():
     assert L.sfgs_fusedssim_forward(1e-4, 9e-4, 1, 3, 8, 8, None, None, 1, None, None, None, None, None) == -2
 
 
+def test_new_option_validation_without_gpu():
+    """ABI v2 options are validated before any CUDA work: backward phases, peer tables, fused activations."""
+    from sfgs import native
+    L = native.lib()
+    b = native.BackwardArgs()
+    b.P, b.width, b.height = 8, 32, 32
+    dummy = (C.c_float * 64)()
+    ptr = C.cast(dummy, C.c_void_p)          # the struct mirrors declare raw pointers as c_void_p
+    b.geom_buffer = b.binning_buffer = b.image_buffer = C.cast(dummy, C.c_void_p)
+    b.phase = 3
+    assert L.sfgs_rasterize_backward(C.byref(b)) == -2 and "phase" in native.last_error()
+    b.phase = 1                                   # phase 1 needs the pixel cotangents and a caller-owned acc (or peers)
+    for f in ("dL_dpix", "dL_dpix_depth", "dL_dpix_norm", "dL_dpix_alpha", "accum_alphas"):
+        setattr(b, f, ptr)
+    assert L.sfgs_rasterize_backward(C.byref(b)) == -2 and "acc" in native.last_error()
+    peers = (C.c_void_p * 2)(C.cast(dummy, C.c_void_p), C.cast(dummy, C.c_void_p))
+    b.acc_peers, b.n_peers, b.peer_slice = C.cast(peers, C.POINTER(C.c_void_p)), 2, 3     # 2*3 < P
+    assert L.sfgs_rasterize_backward(C.byref(b)) == -2 and "acc_peers" in native.last_error()
+    b.n_peers, b.peer_slice = 9, 4                                                          # more than 8 peers
+    assert L.sfgs_rasterize_backward(C.byref(b)) == -2
+    b.phase, b.n_peers = 0, 2                                                               # peers are a phase-1 option
+    assert L.sfgs_rasterize_backward(C.byref(b)) == -2
+    # forward: peer frame blocks are limited to 8
+    a = native.ForwardArgs()
+    a.P, a.width, a.height = 8, 32, 32
+    a.out_peers, a.n_out_peers = C.cast(peers, C.POINTER(C.c_void_p)), 9
+    assert L.sfgs_rasterize_forward(C.byref(a)) == -2
+    # fused activations
+    assert L.sfgs_activations_forward(0, None, None, None, None, None, None, None, None) == 0
+    assert L.sfgs_activations_forward(4, None, None, None, None, None, None, None, None) == -2
+    assert L.sfgs_activations_backward(-1, None, None, None, None, None, None, None, None, None, None, None) == -2
+    assert L.sfgs_activations_backward(4, None, None, None, None, None, None, None, None, None, None, None) == -2
+
+
+def test_activation_wrapper_rejects_cpu_tensors():
+    import torch
+    from sfgs.activations import fused_activations
+    with pytest.raises(ValueError, match="CUDA float32"):
+        fused_activations(torch.zeros(4, 1), torch.zeros(4, 3), torch.zeros(4, 4), torch.zeros(4, 1, dtype=torch.float64))
+
+
 def test_python_wrapper_validation():
     import torch
     from diff_gauss import GaussianRasterizationSettings, GaussianRasterizer
