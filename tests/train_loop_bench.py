@@ -1,6 +1,6 @@
-"""BASELINE.json configs[2] ("train.py-equivalent loop") as a throughput measurement — needs a GPU.
+"""BASELINE.json configs[2] ("train.py-equivalent loop") as a throughput measurement — needs a GPU.  Not a pytest file.
 
-    python tools/train_loop_bench.py [--P 1000000] [--iters 200] [--impl ours|reference|both]
+    python tests/train_loop_bench.py [--P 1000000] [--iters 200] [--impl ours|reference|both]
 
 One iteration = what the reference's train.py does per step around the rasterizer (train.py:195-260):
 activations -> render one of 8 orbit views at 1920x1080 -> 0.8 L1 + 0.2 (1 - SSIM) against an image of a hidden
@@ -16,7 +16,7 @@ import json
 import os
 import sys
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))   # repo root (this file lives in tests/: it uses oracle/_ref)
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "skyfall-gs_b200"))
 import numpy as np
 import torch
