@@ -263,6 +263,11 @@ int sfgs_profile_read(double* ms_total, long long* launches, int n);
  * Used by bench.py to sample clocks in-stream during the timed loop without touching NVML. */
 int sfgs_sm_clock_probe(float* out_mhz_device, void* stream);
 
+/* Self-test hook for the parity tests: y_replica[i] = the expf routine the blend kernels use (csrc/sfgs_common.cuh,
+ * sfgs_expf), y_expf[i] = the compiler's expf(x[i]); the two must agree bit for bit, because the alpha thresholds
+ * that decide n_contrib are evaluated on it. */
+int sfgs_selftest_expf(int n, const float* x, float* y_replica, float* y_expf, void* stream);
+
 /* ---- misc ---------------------------------------------------------------- */
 const char* sfgs_last_error(void);
 /* sizeof() of the ABI structs as compiled (0 forward_args, 1 backward_args, 2 geom_view, 3 image_view,

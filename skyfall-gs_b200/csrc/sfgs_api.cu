@@ -19,7 +19,7 @@
 #include <vector>
 #include "sfgs_common.cuh"
 
-long long g_sfgs_launches = 0;
+std::atomic<long long> g_sfgs_launches{0};
 
 void sfgs_launch_preprocess(const sfgs_forward_args* a, const GeomLayout& g, const ImageLayout& im,
                             const BinningLayout& b, unsigned long long capacity, float focal_x, float focal_y,
@@ -57,9 +57,45 @@ __global__ void sm_clock_probe_kernel(float* out_mhz) {
   *out_mhz = (float)((double)(c1 - c0) * 1000.0 / (double)(t1 - t0));
 }
 
+// self-test hook: the blend kernels' expf replica next to the compiler's expf (tests sweep them for bit equality)
+__global__ void expf_selftest_kernel(int n, const float* __restrict__ x, float* __restrict__ y_replica,
+                                     float* __restrict__ y_expf) {
+  const SfgsExpConsts ek = sfgs_exp_consts(n < 0 ? 1u : 0u);   // a zero the compiler cannot fold, like the kernels' one
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    y_replica[i] = sfgs_expf(x[i], ek);
+    y_expf[i] = exp(x[i]);
+  }
+}
+
 thread_local char t_err[512] = "";
-std::atomic<long long> g_last_R{0};
 std::atomic<long long> g_last_capacity{0};
+
+// Running estimate of the instance count, keyed by what determines it to first order: (device, P, image size, band).
+// A training loop alternates 1080p train views, 1024^2 pseudo-views and low-resolution evaluation renders of the
+// same scene; one process-wide estimate would overflow (and re-run the forward) on every switch upward.
+struct CapKey { int dev, P, W, H, b0, b1; };
+struct CapEntry { CapKey k; long long R; unsigned long long stamp; };
+std::mutex g_cap_mu;
+std::vector<CapEntry> g_cap_tab;
+unsigned long long g_cap_clock = 0;
+constexpr size_t CAP_TAB_MAX = 64;
+bool cap_same(const CapKey& a, const CapKey& b) { return a.dev == b.dev && a.P == b.P && a.W == b.W && a.H == b.H && a.b0 == b.b0 && a.b1 == b.b1; }
+long long cap_lookup(const CapKey& k) {
+  std::lock_guard<std::mutex> lk(g_cap_mu);
+  for (auto& e : g_cap_tab) if (cap_same(e.k, k)) { e.stamp = ++g_cap_clock; return e.R; }
+  return -1;
+}
+void cap_store(const CapKey& k, long long R) {
+  std::lock_guard<std::mutex> lk(g_cap_mu);
+  for (auto& e : g_cap_tab) if (cap_same(e.k, k)) { e.R = R; e.stamp = ++g_cap_clock; return; }
+  if (g_cap_tab.size() >= CAP_TAB_MAX) {   // evict the least recently used entry
+    size_t lru = 0;
+    for (size_t i = 1; i < g_cap_tab.size(); i++) if (g_cap_tab[i].stamp < g_cap_tab[lru].stamp) lru = i;
+    g_cap_tab[lru] = CapEntry{k, R, ++g_cap_clock};
+  } else {
+    g_cap_tab.push_back(CapEntry{k, R, ++g_cap_clock});
+  }
+}
 
 int fail(int code, const char* what, cudaError_t e = cudaSuccess) {
   if (e != cudaSuccess) snprintf(t_err, sizeof(t_err), "%s: %s", what, cudaGetErrorString(e));
@@ -92,9 +128,10 @@ struct StageProf {
   std::vector<Span> pool;
   double ms[ST_COUNT] = {0};
   long long n[ST_COUNT] = {0};
-  cudaEvent_t cur_a = nullptr, cur_b = nullptr;
+  std::mutex mu;   // begin/end may be called from several host threads (one per device)
   void begin(int stage, cudaStream_t st) {
     if (!on) return;
+    std::lock_guard<std::mutex> lk(mu);
     Span s;
     if (!pool.empty()) { s = pool.back(); pool.pop_back(); }
     else { cudaEventCreate(&s.a); cudaEventCreate(&s.b); }
@@ -103,10 +140,13 @@ struct StageProf {
     spans.push_back(s);
   }
   void end(cudaStream_t st) {
-    if (!on || spans.empty()) return;
+    if (!on) return;
+    std::lock_guard<std::mutex> lk(mu);
+    if (spans.empty()) return;
     cudaEventRecord(spans.back().b, st);
   }
   void collect() {
+    std::lock_guard<std::mutex> lk(mu);
     for (auto& s : spans) {
       float t = 0.f;
       if (cudaEventSynchronize(s.b) == cudaSuccess && cudaEventElapsedTime(&t, s.a, s.b) == cudaSuccess) { ms[s.stage] += t; n[s.stage]++; }
@@ -120,19 +160,22 @@ std::mutex g_prof_mu;
 #define PROF_BEGIN(stage) g_prof.begin(stage, st)
 #define PROF_END() g_prof.end(st)
 
+// Pinned landing zone of the image header + the event the host waits on: one per (host thread, device) — a CUDA
+// event belongs to the device that was current when it was created and cannot be recorded on another device's stream.
 struct PinnedHdr {
   uint32_t* p = nullptr;
   cudaEvent_t ev = nullptr;
   ~PinnedHdr() { /* leaked on purpose: the CUDA context may already be gone at exit */ }
   uint32_t* get() {
     if (!p) {
-      if (cudaHostAlloc((void**)&p, IMG_HDR_WORDS * sizeof(uint32_t), cudaHostAllocDefault) != cudaSuccess) p = nullptr;
+      if (cudaHostAlloc((void**)&p, IMG_HDR_WORDS * sizeof(uint32_t), cudaHostAllocPortable) != cudaSuccess) p = nullptr;
       if (p && cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) { ev = nullptr; }
     }
     return (p && ev) ? p : nullptr;
   }
 };
-thread_local PinnedHdr t_hdr;
+constexpr int MAX_DEVICES = 64;
+thread_local PinnedHdr t_hdr_dev[MAX_DEVICES];
 
 }  // namespace
 
@@ -140,7 +183,7 @@ extern "C" {
 
 const char* sfgs_last_error(void) { return t_err; }
 int sfgs_version(void) { return SFGS_VERSION; }
-long long sfgs_launch_count(void) { return g_sfgs_launches; }
+long long sfgs_launch_count(void) { return g_sfgs_launches.load(); }
 long long sfgs_last_capacity(void) { return g_last_capacity.load(); }
 
 size_t sfgs_geom_bytes(int P) { return GeomLayout(nullptr, (size_t)(P > 0 ? P : 0)).bytes; }
@@ -204,11 +247,16 @@ int sfgs_rasterize_forward(const sfgs_forward_args* a) {
   if (!iptr) return fail(SFGS_E_ALLOC, "forward: image allocator returned NULL");
   ImageLayout im(sfgs_align_ptr(iptr), a->width, a->height);
 
+  int dev = 0;
+  CU(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= MAX_DEVICES) return fail(SFGS_E_UNSUPPORTED, "forward: device ordinal >= 64");
+  const CapKey cap_key{dev, P, a->width, a->height, a->tile_row_begin, a->tile_row_end};
   long long capacity = a->capacity_hint;
   if (capacity <= 0) {
-    const long long last = g_last_R.load();
-    capacity = last > 0 ? last + last / 4 + 4096 : (long long)P * 4 + 65536;
+    const long long last = cap_lookup(cap_key);
+    capacity = last >= 0 ? last + last / 4 + 4096 : (long long)P * 4 + 65536;
   }
+  PinnedHdr& t_hdr = t_hdr_dev[dev];
   uint32_t* hhdr = t_hdr.get();
   if (!hhdr) return fail(SFGS_E_CUDA, "forward: pinned header allocation failed");
 
@@ -256,11 +304,14 @@ int sfgs_rasterize_forward(const sfgs_forward_args* a) {
     CU(cudaEventSynchronize(t_hdr.ev));
     if (debug) CU(cudaStreamSynchronize(st));
     R = (long long)hhdr[HDR_R];
+    // the reference's checkFrustum traps the kernel when `prefiltered` is set and a point fails the test
+    // (RAST/cuda_rasterizer/auxiliary.h:157-161); here the frame is reported as an argument error instead
+    if (hhdr[HDR_PREFILTER]) return fail(SFGS_E_BADARG, "forward: prefiltered was set but a Gaussian failed the frustum test");
     if (!hhdr[HDR_OVERFLOW]) break;
     if (attempt == 2) return fail(SFGS_E_CUDA, "forward: binning capacity overflow persisted");
     capacity = R + R / 16 + 4096;   // the exact count is now known; run the pipeline again with room for it
   }
-  g_last_R.store(R);
+  cap_store(cap_key, R);
   g_last_capacity.store(capacity);
   return (int)R;
 }
@@ -278,7 +329,12 @@ int sfgs_rasterize_backward(const sfgs_backward_args* a) {
   if (do_gauss && (!a->dL_dmean2D || !a->dL_dconic || !a->dL_dopacity || !a->dL_dcolor || !a->dL_ddepth || !a->dL_dmean3D ||
                    !a->dL_dcov3D || !a->dL_dnorm3D || !a->dL_dscale || !a->dL_drot))
     return fail(SFGS_E_BADARG, "backward: null output");
+  if (do_gauss && !a->radii) return fail(SFGS_E_BADARG, "backward: radii missing");
   if (do_gauss && a->M > 0 && a->shs && !a->dL_dsh) return fail(SFGS_E_BADARG, "backward: dL_dsh missing");
+  // extra-attribute gradients are accumulated by the blend stage only and are never exchanged between ranks: the
+  // two-phase (multi-GPU) form would return them partial or uninitialised
+  if (a->ED > 0 && phase != 0) return fail(SFGS_E_UNSUPPORTED, "backward: extra_attrs are not supported by the two-phase backward");
+  if (a->tile_row_begin < 0 || a->tile_row_end < a->tile_row_begin) return fail(SFGS_E_BADARG, "backward: bad tile-row band");
   if (a->ED > 0 && (!a->dL_dextra || !a->dL_dpix_extra || !a->extra_attrs)) return fail(SFGS_E_BADARG, "backward: extra attrs missing");
   const bool peer = a->acc_peers != nullptr;
   if (peer && (phase != 1 || a->n_peers < 1 || a->n_peers > 8 || a->peer_slice < 1 ||
@@ -368,6 +424,15 @@ int sfgs_activations_backward(int P, const float* opacity_raw, const float* scal
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(SFGS_E_CUDA, "activations_backward", e);
   return SFGS_OK;
+}
+
+int sfgs_selftest_expf(int n, const float* x, float* y_replica, float* y_expf, void* stream) {
+  if (n < 0 || (n > 0 && (!x || !y_replica || !y_expf))) return fail(SFGS_E_BADARG, "selftest_expf: bad arguments");
+  if (n == 0) return SFGS_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  expf_selftest_kernel<<<592, 256, 0, st>>>(n, x, y_replica, y_expf);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? SFGS_OK : fail(SFGS_E_CUDA, "selftest_expf", e);
 }
 
 int sfgs_sm_clock_probe(float* out_mhz_device, void* stream) {

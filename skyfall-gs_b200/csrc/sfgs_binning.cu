@@ -280,10 +280,9 @@ void sfgs_launch_scatter(const ImageLayout& im, const BinningLayout& b, unsigned
 
 void sfgs_launch_tile_sort(const GeomLayout& g, const ImageLayout& im, const BinningLayout& b, cudaStream_t st) {
   constexpr size_t smem_light = 2 * 1024 * sizeof(uint64_t), smem_heavy = 2 * 4096 * sizeof(uint64_t);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static SfgsPerDeviceOnce attr_once;   // function attributes are per device
+  if (attr_once.first_use()) {
     cudaFuncSetAttribute(tile_sort_kernel<256, 4096, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_heavy);
-    attr_set = true;
   }
   SFGS_COUNT_LAUNCH();
   tile_sort_kernel<128, 1024, 0><<<im.tiles, 128, smem_light, st>>>(im.ranges, im.hdr, b.keys, b.keys_tmp, b.point_list,

@@ -135,39 +135,61 @@ __device__ __forceinline__ float4 cov2d_project(float mx, float my, float mz,
   return make_float4(c00, c01, c11, coef);
 }
 
-// SH -> RGB (+0.5, clamp at 0 with mask). Mirrors computeColorFromSH, forward.cu:20-71.
+// SH -> RGB (+0.5, clamp at 0 with mask).  Follows computeColorFromSH, forward.cu:20-71.
+//
+// The clamp flag (colour < 0 before the clamp) is CONTROL FLOW of the backward pass: a colour within an ulp of zero
+// that lands on the other side flips dL/dSH of that channel between 0 and its full value (seen once in a 5M-Gaussian
+// frame while the colour itself only differed by 1e-7).  So this routine is evaluated exactly like the reference's
+// binary evaluates it — every multiply / add / fused multiply-add below is the one in the reference's sm_100a SASS
+// (read off oracle/_ref, preprocessCUDA<3>, section after the three IEEE divisions of the view direction), pinned
+// with round-to-nearest intrinsics so the compiler cannot contract it differently: colours, and therefore the clamp
+// flags, are bit-identical to the reference (tests: rgb compared bit for bit on every visible Gaussian).
 __device__ __forceinline__ void sh_to_rgb(int deg, const float* __restrict__ sh /* [M][3] */,
                                           float px, float py, float pz, float cx, float cy, float cz,
                                           float rgb[3], unsigned& clamp_mask) {
-  float dx = px - cx, dy = py - cy, dz = pz - cz;
-  const float len = sqrt(dx * dx + dy * dy + dz * dz);
-  dx = dx / len; dy = dy / len; dz = dz / len;
-  float res[3];
-#pragma unroll
-  for (int ch = 0; ch < 3; ch++) {
-    float r = SH_C0 * sh[0 * 3 + ch];
-    if (deg > 0) {
-      const float x = dx, y = dy, z = dz;
-      r = r - SH_C1 * y * sh[1 * 3 + ch] + SH_C1 * z * sh[2 * 3 + ch] - SH_C1 * x * sh[3 * 3 + ch];
-      if (deg > 1) {
-        const float xx = x * x, yy = y * y, zz = z * z;
-        const float xy = x * y, yz = y * z, xz = x * z;
-        r = r + SH_C2_0 * xy * sh[4 * 3 + ch] + SH_C2_1 * yz * sh[5 * 3 + ch] +
-            SH_C2_2 * (2.0f * zz - xx - yy) * sh[6 * 3 + ch] + SH_C2_3 * xz * sh[7 * 3 + ch] +
-            SH_C2_4 * (xx - yy) * sh[8 * 3 + ch];
-        if (deg > 2) {
-          r = r + SH_C3_0 * y * (3.0f * xx - yy) * sh[9 * 3 + ch] + SH_C3_1 * xy * z * sh[10 * 3 + ch] +
-              SH_C3_2 * y * (4.0f * zz - xx - yy) * sh[11 * 3 + ch] +
-              SH_C3_3 * z * (2.0f * zz - 3.0f * xx - 3.0f * yy) * sh[12 * 3 + ch] +
-              SH_C3_4 * x * (4.0f * zz - xx - yy) * sh[13 * 3 + ch] + SH_C3_5 * z * (xx - yy) * sh[14 * 3 + ch] +
-              SH_C3_6 * x * (xx - 3.0f * yy) * sh[15 * 3 + ch];
-        }
+  const float dx = __fsub_rn(px, cx), dy = __fsub_rn(py, cy), dz = __fsub_rn(pz, cz);
+  // glm::length: dot = (x*x + y*y) + z*z, contracted as fma(z, z, fma(x, x, y*y))
+  const float len = __fsqrt_rn(__fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy))));
+  const float x = __fdiv_rn(dx, len), y = __fdiv_rn(dy, len), z = __fdiv_rn(dz, len);
+  float c[16];   // basis value times its constant, in the reference's association order
+  c[0] = SH_C0;
+  if (deg > 0) {
+    c[1] = -__fmul_rn(y, SH_C1); c[2] = __fmul_rn(z, SH_C1); c[3] = -__fmul_rn(x, SH_C1);
+    if (deg > 1) {
+      const float xx = __fmul_rn(x, x), yy = __fmul_rn(y, y), zz = __fmul_rn(z, z);
+      const float xy = __fmul_rn(x, y), yz = __fmul_rn(y, z), xz = __fmul_rn(x, z);
+      const float zz2 = __fadd_rn(zz, zz);                                  // 2 zz (exact)
+      const float xx_m_yy = __fsub_rn(xx, yy);
+      c[4] = __fmul_rn(xy, SH_C2_0);
+      c[5] = __fmul_rn(yz, SH_C2_1);
+      c[6] = __fmul_rn(__fsub_rn(__fsub_rn(zz2, xx), yy), SH_C2_2);         // (2zz - xx) - yy
+      c[7] = __fmul_rn(xz, SH_C2_3);
+      c[8] = __fmul_rn(xx_m_yy, SH_C2_4);
+      if (deg > 2) {
+        const float zz4_m_xx_m_yy = __fsub_rn(__fmaf_rn(zz, 4.0f, -xx), yy);                    // fma(zz, 4, -xx) - yy
+        c[9] = __fmul_rn(__fmul_rn(y, SH_C3_0), __fmaf_rn(xx, 3.0f, -yy));                       // fma(xx, 3, -yy)
+        c[10] = __fmul_rn(__fmul_rn(xy, SH_C3_1), z);
+        c[11] = __fmul_rn(__fmul_rn(y, SH_C3_2), zz4_m_xx_m_yy);
+        c[12] = __fmul_rn(__fmul_rn(z, SH_C3_3), __fmaf_rn(yy, -3.0f, __fmaf_rn(xx, -3.0f, zz2)));   // (2zz - 3xx) - 3yy
+        c[13] = __fmul_rn(zz4_m_xx_m_yy, __fmul_rn(x, SH_C3_4));
+        c[14] = __fmul_rn(xx_m_yy, __fmul_rn(z, SH_C3_5));
+        c[15] = __fmul_rn(__fmul_rn(x, SH_C3_6), __fmaf_rn(yy, -3.0f, xx));                      // fma(yy, -3, xx)
       }
     }
-    res[ch] = r + 0.5f;
   }
-  clamp_mask = (res[0] < 0 ? 1u : 0u) | (res[1] < 0 ? 2u : 0u) | (res[2] < 0 ? 4u : 0u);
-  rgb[0] = fmaxf(res[0], 0.0f); rgb[1] = fmaxf(res[1], 0.0f); rgb[2] = fmaxf(res[2], 0.0f);
+  const int ncoef = (deg + 1) * (deg + 1);
+  clamp_mask = 0u;
+#pragma unroll
+  for (int ch = 0; ch < 3; ch++) {
+    float r = __fmul_rn(sh[ch], SH_C0);
+#pragma unroll
+    for (int k = 1; k < 16; k++)
+      if (k < ncoef) r = __fmaf_rn(c[k], sh[3 * k + ch], r);      // one fused multiply-add per coefficient, in order
+    // result += 0.5; clamped = result < 0; result = max(result, 0)   (forward.cu:63-70; the binary tests r < -0.5)
+    const float v = __fadd_rn(r, 0.5f);
+    if (v < 0.0f) clamp_mask |= 1u << ch;
+    rgb[ch] = (v < 0.0f) ? 0.0f : v;
+  }
 }
 
 constexpr int PRE_THREADS = 256;
@@ -383,10 +405,9 @@ void sfgs_launch_preprocess(const sfgs_forward_args* a, const GeomLayout& g, con
                             cudaStream_t st) {
   const int blocks = (a->P + PRE_THREADS - 1) / PRE_THREADS;
   constexpr size_t smem = PRE_THREADS * (12 * sizeof(float4) + sizeof(uint32_t) + sizeof(int4));
-  static bool attr_set = false;
-  if (!attr_set) {
+  static SfgsPerDeviceOnce attr_once;   // function attributes are per device
+  if (attr_once.first_use()) {
     cudaFuncSetAttribute(preprocess_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attr_set = true;
   }
   SFGS_COUNT_LAUNCH();
   preprocess_kernel<<<blocks, PRE_THREADS, smem, st>>>(

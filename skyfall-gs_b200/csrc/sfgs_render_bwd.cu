@@ -187,7 +187,7 @@ render_bwd_kernel(const uint2* __restrict__ ranges, const char* __restrict__ bin
 #pragma unroll
       for (int blk = 0; blk < BWD_WARPS; blk++) {
         const unsigned word = __ballot_sync(0xffffffffu, (m >> blk) & 1u);
-        if (lane == 0) S.bits[bstage][blk][wid] = word;
+        if (lane == 0) S.bits[bstage][blk][wid] = __brev(word);   // bit 31 = record 0 of the word (see the walk below)
       }
     }
   };
@@ -245,6 +245,7 @@ render_bwd_kernel(const uint2* __restrict__ ranges, const char* __restrict__ bin
     __syncwarp();
   };
 
+  const SfgsExpConsts ek = sfgs_exp_consts(hdr[HDR_ZERO]);
   issue(0, 0, 0);
   int kcur = 0;     // fill level of this warp's chunk; a chunk may span two consecutive batches
   int cbirth = 0;   // batch in which the chunk's first record was staged
@@ -260,24 +261,29 @@ render_bwd_kernel(const uint2* __restrict__ ranges, const char* __restrict__ bin
     if (e0 < 0) e0 = 0;
     for (int word = e0 >> 5; word < BWD_BATCH / 32; word++) {
       unsigned bits = S.bits[bstage][wid][word];
-      if (word == (e0 >> 5)) bits &= 0xffffffffu << (e0 & 31);
+      if (word == (e0 >> 5)) bits &= 0xffffffffu >> (e0 & 31);   // bit 31 - (e & 31) <-> record e: drop e < e0
+      // record 32*word + 31 - kk: kk records below this ring pointer, kk positions above this list position
+      const float4* rec_hi = &S.rec[stage][word * 32 + 31][0];
+      const int e_hi = word * 32 + 31;
       while (bits) {
-        const int e = word * 32 + __ffs(bits) - 1;
-        bits &= bits - 1;
-        const int pos = first_pos - e;
-        const float4 ra = S.rec[stage][e][0];   // mx, my, con.x, con.y
-        const float4 rb = S.rec[stage][e][1];   // con.z, opac, depth
+        unsigned kk;
+        asm("bfind.u32 %0, %1;" : "=r"(kk) : "r"(bits));   // FLO: highest set bit = next record back to front
+        bits ^= ek.one << kk;
+        const float4* rp = rec_hi - 4 * kk;
+        const int pos = first_pos - e_hi + (int)kk;
+        const float4 ra = rp[0];   // mx, my, con.x, con.y
+        const float4 rb = rp[1];   // con.z, opac, depth
         const float dx = ra.x - pixfx, dy = ra.y - pixfy;
         const float power = -0.5f * (ra.z * dx * dx + rb.x * dy * dy) - ra.w * dx * dy;
-        const float G = exp(power);
+        const float G = sfgs_expf(power, ek);
         const float alpha = min(0.99f, rb.y * G);
         const bool active = ((uint32_t)pos < last_contributor) && !(power > 0.0f) && !(alpha < 1.0f / 255.0f);
         if (!__any_sync(0xffffffffu, active)) continue;
 
         float w_out = 0.f, h_out = 0.f;
         if (active) {
-          const float4 rc = S.rec[stage][e][2];   // r, g, b, nx
-          const float4 rd = S.rec[stage][e][3];   // ny, nz
+          const float4 rc = rp[2];   // r, g, b, nx
+          const float4 rd = rp[3];   // ny, nz
           // 1 - alpha is in [0.01, 1]: the approximate reciprocal (1 ulp, one MUFU) needs no range fix-up; it is shared
           // by the T recovery and the background term
           float inv_1ma;
@@ -294,7 +300,7 @@ render_bwd_kernel(const uint2* __restrict__ ranges, const char* __restrict__ bin
           g_last = g;
           float dL_dalpha = g - A;
           if (HAS_EXTRA) {
-            const uint32_t gid = S.id[stage][e];
+            const uint32_t gid = S.id[stage][e_hi - (int)kk];
             for (int ch = 0; ch < ED; ch++) {
               const float ex = extras[(size_t)gid * ED + ch];
               accum_ree[ch] = last_alpha * last_extra[ch] + (1.f - last_alpha) * accum_ree[ch];
@@ -311,7 +317,7 @@ render_bwd_kernel(const uint2* __restrict__ ranges, const char* __restrict__ bin
         }
         S.wh[wid][lane][kcur] = make_float2(w_out, h_out);
         // the record itself stays in the staging ring; the chunk slot only remembers where
-        if (lane == 0) S.cref[wid][kcur] = (uint32_t)(stage * BWD_BATCH + e);
+        if (lane == 0) S.cref[wid][kcur] = (uint32_t)(stage * BWD_BATCH + e_hi) - kk;
         if (kcur == 0) cbirth = b;
         if (++kcur == CH) { phase2(CH); kcur = 0; }
       }
@@ -331,13 +337,12 @@ void sfgs_launch_render_bwd(const sfgs_backward_args* a, const GeomLayout& g, co
   if (band1 <= band0) return;
   dim3 grid(im.tiles_x, band1 - band0, 1);
   const size_t smem = sizeof(BwdSmem);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static SfgsPerDeviceOnce attr_once;   // function attributes are per device
+  if (attr_once.first_use()) {
     cudaFuncSetAttribute(render_bwd_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaFuncSetAttribute(render_bwd_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaFuncSetAttribute(render_bwd_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaFuncSetAttribute(render_bwd_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attr_set = true;
   }
   PeerTable pt = {};
   const bool peer = a->acc_peers != nullptr && a->n_peers > 0;

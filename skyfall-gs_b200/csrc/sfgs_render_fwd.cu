@@ -102,15 +102,19 @@ render_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
   const int total = (int)(range.y - range.x);
   const int nbatches = (total + FWD_BATCH - 1) / FWD_BATCH;
 
-  float T = 1.0f;
-  uint32_t contributor = 0, last_contributor = 0;
+  // Transmittance of a live pixel.  A pixel that is finished (outside the image, or its next T would drop below
+  // 1e-4) parks its transmittance in T_done and continues with T = 0: every later record then fails the same
+  // `T*(1-alpha) < 1e-4` test on its own, so the inner loop needs no separate per-lane "done" flag (a live T is
+  // never 0: it starts at 1, shrinks by factors >= 0.01 and stops before it reaches 1e-4).
+  float T = inside ? 1.0f : 0.0f;
+  float T_done = 0.0f;
+  uint32_t last_contributor = 0;
   float C0 = 0.f, C1 = 0.f, C2 = 0.f, Dp = 0.f, N0 = 0.f, N1 = 0.f, N2 = 0.f;
   float E[HAS_EXTRA ? SFGS_MAX_EXTRA : 1];
   if (HAS_EXTRA) {
 #pragma unroll
     for (int i = 0; i < SFGS_MAX_EXTRA; i++) E[i] = 0.f;
   }
-  bool done = !inside;
 
 #if SFGS_TMA_STAGING
   __shared__ __align__(8) unsigned long long s_mbar[FWD_STAGES];
@@ -124,7 +128,8 @@ render_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
 #endif
 
   // stage loader: thread t copies record t of the batch (skipped when no block of the tile can be reached) and
-  // the warp publishes, per pixel block, the ballot of "this record reaches the block".
+  // the warp publishes, per pixel block, the ballot of "this record reaches the block" — bit-REVERSED, so that the
+  // walk below finds the next record with one count-leading-zeros (FLO) instead of a bit reversal + FLO per record.
   auto issue = [&](int batch, int stage) {
     const int e = batch * FWD_BATCH + tid;
     unsigned m = 0;
@@ -156,10 +161,11 @@ render_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
 #pragma unroll
     for (int blk = 0; blk < FWD_THREADS / 32; blk++) {
       const unsigned word = __ballot_sync(0xffffffffu, (m >> blk) & 1u);
-      if (lane == 0) s_bits[stage][blk][wid] = word;
+      if (lane == 0) s_bits[stage][blk][wid] = __brev(word);
     }
   };
 
+  const SfgsExpConsts ek = sfgs_exp_consts(hdr[HDR_ZERO]);
   if (nbatches > 0) issue(0, 0);
   for (int b = 0; b < nbatches; b++) {
     const int stage = b & 1;
@@ -169,41 +175,46 @@ render_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
     cp_async_wait<0>();
 #endif
     // barrier: stage `b` visible to all, stage `b^1` no longer read by anyone
-    const int num_done = __syncthreads_count(done);
+    const int num_done = __syncthreads_count(T == 0.0f);
     if (num_done == FWD_THREADS) break;
     if (b + 1 < nbatches) issue(b + 1, stage ^ 1);
     for (int word = 0; word < FWD_BATCH / 32; word++) {
       unsigned m = s_bits[stage][wid][word];
       if (m == 0u) continue;
-      if (__all_sync(0xffffffffu, done)) break;
+      if (__all_sync(0xffffffffu, T == 0.0f)) break;
+      // bit 31 = first record of the word: record 32*word + 31 - kk sits kk records BELOW this pointer / position
+      const float4* rec_hi = &s_rec[stage][word * 32 + 31][0];
+      const uint32_t pos_hi = (uint32_t)(b * FWD_BATCH + word * 32 + 32);   // 1-based list position of that record
       while (m) {
-        const int j = word * 32 + __ffs(m) - 1;
-        m &= m - 1;
-        if (done) continue;
-        contributor = (uint32_t)(b * FWD_BATCH + j + 1);
-        const float4 a = s_rec[stage][j][0];   // mx, my, con.x, con.y
-        const float4 c = s_rec[stage][j][1];   // con.z, opac, depth, -
+        unsigned kk;
+        asm("bfind.u32 %0, %1;" : "=r"(kk) : "r"(m));   // FLO: highest set bit = next record front to back
+        m ^= ek.one << kk;
+        const float4* rp = rec_hi - 4 * kk;
+        const float4 a = rp[0];   // mx, my, con.x, con.y
+        const float4 c = rp[1];   // con.z, opac, depth, -
         const float dx = a.x - pixfx, dy = a.y - pixfy;
         const float power = -0.5f * (a.z * dx * dx + c.x * dy * dy) - a.w * dx * dy;
         if (power > 0.0f) continue;
-        const float alpha = min(0.99f, c.y * exp(power));
+        const float alpha = min(0.99f, c.y * sfgs_expf(power, ek));
         if (alpha < 1.0f / 255.0f) continue;
         const float test_T = T * (1 - alpha);
-        if (test_T < 0.0001f) { done = true; continue; }
-        const float4 f = s_rec[stage][j][2];   // r, g, b, nx
-        const float4 g = s_rec[stage][j][3];   // ny, nz
-        C0 += f.x * alpha * T; C1 += f.y * alpha * T; C2 += f.z * alpha * T;
-        Dp += c.z * alpha * T;
-        N0 += f.w * alpha * T; N1 += g.x * alpha * T; N2 += g.y * alpha * T;
+        if (test_T < 0.0001f) { T_done = fmaxf(T_done, T); T = 0.0f; continue; }
+        const float4 f = rp[2];   // r, g, b, nx
+        const float4 g = rp[3];   // ny, nz
+        const float w = alpha * T;
+        C0 = fmaf(f.x, w, C0); C1 = fmaf(f.y, w, C1); C2 = fmaf(f.z, w, C2);
+        Dp = fmaf(c.z, w, Dp);
+        N0 = fmaf(f.w, w, N0); N1 = fmaf(g.x, w, N1); N2 = fmaf(g.y, w, N2);
         if (HAS_EXTRA) {
-          const float* ex = extras + (size_t)s_id[stage][j] * ED;
+          const float* ex = extras + (size_t)s_id[stage][word * 32 + 31 - (int)kk] * ED;
           for (int ch = 0; ch < ED; ch++) E[ch] += ex[ch] * alpha * T;
         }
         T = test_T;
-        last_contributor = contributor;
+        last_contributor = pos_hi - kk;
       }
     }
   }
+  if (T == 0.0f) T = T_done;   // finished early: the transmittance it finished with
 
   if (inside) {
     const size_t HW = (size_t)H * W;

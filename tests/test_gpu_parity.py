@@ -1,6 +1,7 @@
 """GPU parity tests (run with `-m gpu` on a B200): the CUDA path through the C ABI against
   (1) the unmodified reference CUDA rasterizer (oracle/_ref) — bit-exact tile/key indexing, 1e-5 images,
-      gradients within the reference's own atomic-order noise,
+      gradients adjudicated by a float64 evaluation of the reference's algorithm (helpers.adjudicate_gradients:
+      our error against float64 <= 2x the reference build's own error + 1e-5, every element, no outlier budget),
   (2) the CPU oracle (oracle/sfgs_oracle.c),
   (3) the committed golden fixtures produced by the reference on a B200 (tests/golden/ref_*.npz),
 plus edge cases and size-independent properties at the BASELINE.json full size.
@@ -27,21 +28,6 @@ def ref_available():
 
 def bits(t):
     return t.contiguous().view(torch.int32) if t.dtype.is_floating_point else t
-
-
-def grad_close(ours, ref, spread, name, min_bad=4, frac_bad=2e-4, worst_rel=1e-3):
-    """|ours - ref| <= 1e-5 + 1e-4 |ref| + 4 * (reference-vs-reference spread of this tensor) for all but a
-    2e-4 fraction of the elements: the spread is estimated from only two runs of the (atomics-ordered,
-    non-deterministic) reference, so single elements may legitimately exceed four times it."""
-    ours, ref = ours.double().flatten(), ref.double().flatten()
-    assert ours.shape == ref.shape, name
-    if ref.numel() == 0:
-        return
-    tol = 1e-5 + 1e-4 * ref.abs() + 4.0 * float(spread) + 2e-6 * float(ref.abs().max())
-    bad = (ours - ref).abs() > tol
-    # a handful of elements (one Gaussian's worth on a small tensor) may exceed it where large terms cancel
-    assert int(bad.sum()) <= max(min_bad, int(frac_bad * bad.numel())), f"{name}: {int(bad.sum())} of {bad.numel()} beyond tolerance, worst {float((ours - ref).abs().max())}"
-    assert float((ours - ref).abs().max()) <= worst_rel * (1.0 + float(ref.abs().max())), f"{name}: worst {float((ours - ref).abs().max())} vs max |ref| {float(ref.abs().max())}"
 
 
 def run_pair(scene, cam, dev, bg=(0.1, 0.2, 0.3), colors=None, **kw):
@@ -84,13 +70,14 @@ def test_forward_bit_exact_indexing_vs_reference(cuda_device, case):
     assert torch.equal(oi["point_list"], ri["point_list"])
     assert torch.equal(Hh.ref_style_keys(oi["ranges"], oi["keys"]), ri["keys"])
     assert torch.equal(oi["n_contrib"], ri["n_contrib"])
-    assert (oi["rgb"][vis] - ri["rgb"][vis]).abs().max() < 1e-6 if colors is None else True
+    if colors is None:
+        assert torch.equal(bits(oi["rgb"][vis]), bits(ri["rgb"][vis]))     # colours, hence clamp flags, bit for bit
     for k in ("color", "depth", "norm", "alpha"):
         assert (ours[k] - ref[k]).abs().max().item() <= IMG_ATOL, k
 
 
 @pytest.mark.parametrize("case", ["blob", "city"])
-def test_backward_vs_reference_within_its_own_noise(cuda_device, case):
+def test_backward_vs_reference_adjudicated_by_float64(cuda_device, case):
     if not ref_available():
         pytest.skip("oracle/_ref not built")
     dev = cuda_device
@@ -100,11 +87,12 @@ def test_backward_vs_reference_within_its_own_noise(cuda_device, case):
         scene, cam = S.city_scene(300_000, seed=3), S.jax004_camera(1920, 1080)
     d, bg_t, col, ours, ref = run_pair(scene, cam, dev)
     cot = [torch.from_numpy(c).to(dev) for c in S.cotangents(cam.width, cam.height, seed=4)]
+    from oracle import ref_cuda
     gb = Hh.run_ours_backward(d, cam, scene.sh_degree, bg_t, ours, cot)
-    r1 = Hh.run_ref_backward(d, cam, scene.sh_degree, bg_t, ref, cot)
-    r2 = Hh.run_ref_backward(d, cam, scene.sh_degree, bg_t, ref, cot)
-    for k in ("means2D", "colors", "opacity", "means3D", "cov3D", "norm3D", "sh", "scales", "rot"):
-        grad_close(gb[k], r1[k], (r1[k] - r2[k]).abs().max().item(), k)
+    r1 = [Hh.run_ref_backward(d, cam, scene.sh_degree, bg_t, ref, cot) for _ in range(3)]
+    ri = ref_cuda.internals(ref, scene.P, cam.height, cam.width)
+    Hh.adjudicate_gradients(d, cam, scene.sh_degree, bg_t, ri, ref["alpha"], ref["radii"], cot, gb, r1,
+                            f"backward_vs_reference[{case}]")
     # culled Gaussians get exact zeros
     inv = ours["radii"] == 0
     for k in ("means2D", "opacity", "means3D", "sh", "scales", "rot"):
@@ -115,7 +103,7 @@ def test_backward_vs_reference_within_its_own_noise(cuda_device, case):
 def test_randomised_differential_vs_reference(cuda_device, seed):
     """Seeded random configurations (image sizes off the tile grid, every SH degree, scale modifiers, filter sizes,
     backgrounds, cluster tightness) against the unmodified reference CUDA rasterizer: indexing bit-exact, images
-    within 1e-5, gradients within the reference's own atomic noise."""
+    within 1e-5, gradients adjudicated by the float64 evaluation (helpers.adjudicate_gradients)."""
     if not ref_available():
         pytest.skip("oracle/_ref not built")
     from oracle import ref_cuda
@@ -138,14 +126,10 @@ def test_randomised_differential_vs_reference(cuda_device, seed):
         assert (ours[k] - ref[k]).abs().max().item() <= IMG_ATOL, k
     cot = [torch.from_numpy(c).to(dev) for c in S.cotangents(W, H, seed=seed)]
     gb = Hh.run_ours_backward(d, cam, deg, bg_t, ours, cot, kernel_size=kw["kernel_size"], scale_modifier=kw["scale_modifier"])
-    r1 = Hh.run_ref_backward(d, cam, deg, bg_t, ref, cot, kernel_size=kw["kernel_size"], scale_modifier=kw["scale_modifier"])
-    r2 = Hh.run_ref_backward(d, cam, deg, bg_t, ref, cot, kernel_size=kw["kernel_size"], scale_modifier=kw["scale_modifier"])
-    r3 = Hh.run_ref_backward(d, cam, deg, bg_t, ref, cot, kernel_size=kw["kernel_size"], scale_modifier=kw["scale_modifier"])
-    # small tensors, tight clusters (long per-pixel lists, heavy cancellation in the covariance / rotation chain):
-    # the spread is taken over three reference runs and a few more outliers are tolerated than in the large-scene tests
-    for k in ("means2D", "colors", "opacity", "means3D", "cov3D", "norm3D", "sh", "scales", "rot"):
-        spread = max((r1[k] - r2[k]).abs().max().item(), (r1[k] - r3[k]).abs().max().item())
-        grad_close(gb[k], r1[k], spread, k, min_bad=12, frac_bad=1e-3, worst_rel=5e-3)
+    r1 = [Hh.run_ref_backward(d, cam, deg, bg_t, ref, cot, kernel_size=kw["kernel_size"],
+                              scale_modifier=kw["scale_modifier"]) for _ in range(3)]
+    Hh.adjudicate_gradients(d, cam, deg, bg_t, ri, ref["alpha"], ref["radii"], cot, gb, r1, f"randomised[{seed}]",
+                            kernel_size=kw["kernel_size"], scale_modifier=kw["scale_modifier"])
 
 
 @pytest.mark.parametrize("name", CASES)
@@ -172,8 +156,13 @@ def test_against_golden_fixtures(cuda_device, name):
     cot = [torch.from_numpy(c).to(dev) for c in kw["cot"]]
     gb = Hh.run_ours_backward(d, cam, kw["sh_degree"], bg_t, f, cot, kernel_size=kw["kernel_size"],
                               scale_modifier=kw["scale_modifier"], colors=col)
-    for k in ("means2D", "colors", "opacity", "means3D", "cov3D", "norm3D", "sh", "scales", "rot"):
-        grad_close(gb[k].cpu(), torch.from_numpy(g["grad_" + k]), float(g["gradspread_" + k]), k)
+    # the fixture holds one run of the reference CUDA build's gradients; whose error a deviation is, is decided by
+    # the float64 adjudicator on this library's forward intermediates (asserted bit-identical on indexing above)
+    ref_g = {k: torch.from_numpy(g["grad_" + k]).to(dev) for k in ("means2D", "colors", "opacity", "means3D", "cov3D",
+                                                                  "norm3D", "sh", "scales", "rot")}
+    Hh.adjudicate_gradients(d, cam, kw["sh_degree"], bg_t, it, f["alpha"], f["radii"], cot, gb, ref_g,
+                            f"golden[{name}]", kernel_size=kw["kernel_size"], scale_modifier=kw["scale_modifier"],
+                            colors=col)
 
 
 def test_against_cpu_oracle(cuda_device):
@@ -550,3 +539,87 @@ def test_training_loop_with_all_three_ops(cuda_device):
         opt.step()
         losses.append(loss.item())
     assert np.mean(losses[-8:]) < 0.7 * np.mean(losses[:4]), (losses[:4], losses[-8:])
+
+
+# ----------------------------------------------------------------------------- the configurations that are benched
+def _benched_config(name):
+    """(scene, camera) of every frame bench.py reports a number on (BASELINE.json configs[1] and configs[3], plus the
+    SURVEY 8d whole-scene orbit stress frame and the dense 5M variant the round-1 numbers were quoted on)."""
+    if name == "configs1_1M_jax004":       # bench.py's headline frame, exactly
+        return S.city_scene(1_000_000, seed=0), S.jax004_camera(1920, 1080)
+    if name == "configs1_1M_orbit":        # SURVEY 8d second camera: fov 60, radius 300, elevation 85
+        return S.city_scene(1_000_000, seed=0), S.orbit_camera(width=1920, height=1080)
+    if name == "configs3_5M_jax004":       # SURVEY 8d config 4: same generator, extent x sqrt(5)
+        return S.city_scene(5_000_000, seed=0, extent=256.0 * 5 ** 0.5), S.jax004_camera(1920, 1080)
+    if name == "dense_5M_jax004":          # 5x the density of configs[1] in the same extent (long tile lists)
+        return S.city_scene(5_000_000, seed=0), S.jax004_camera(1920, 1080)
+    raise KeyError(name)
+
+
+@pytest.mark.parametrize("name", ["configs1_1M_jax004", "configs1_1M_orbit", "configs3_5M_jax004", "dense_5M_jax004"])
+def test_benched_configurations_vs_reference(cuda_device, name):
+    """The frames bench.py times, diffed against the unmodified reference CUDA build at full size: every indexing
+    quantity bit for bit (radii, tiles_touched, depth bits / means2D / conic, ranges, point_list, keys, n_contrib),
+    the four images within 1e-5, all nine gradient tensors adjudicated by the float64 evaluation."""
+    if not ref_available():
+        pytest.skip("oracle/_ref not built")
+    from oracle import ref_cuda
+    dev = cuda_device
+    scene, cam = _benched_config(name)
+    d, bg_t, col, ours, ref = run_pair(scene, cam, dev, bg=(0.0, 0.0, 0.0))
+    P, H, W = scene.P, cam.height, cam.width
+    assert ours["num_rendered"] == ref["num_rendered"]
+    assert torch.equal(ours["radii"], ref["radii"])
+    oi, ri = Hh.our_internals(ours, P, H, W), ref_cuda.internals(ref, P, H, W)
+    vis = ref["radii"] > 0
+    assert torch.equal(oi["tiles_touched"], ri["tiles_touched"])
+    for k in ("depths", "means2D", "cov3D", "conic_opacity"):
+        assert torch.equal(bits(oi[k][vis]), bits(ri[k][vis])), k
+    assert torch.equal(oi["ranges"], ri["ranges"])
+    assert torch.equal(oi["point_list"], ri["point_list"])
+    assert torch.equal(Hh.ref_style_keys(oi["ranges"], oi["keys"]), ri["keys"])
+    assert torch.equal(oi["n_contrib"], ri["n_contrib"])
+    assert torch.equal(bits(oi["rgb"][vis]), bits(ri["rgb"][vis]))         # colours, hence clamp flags, bit for bit
+    ours_clamped = torch.stack([(oi["clamped"] >> k) & 1 for k in range(3)], 1).bool()
+    assert torch.equal(ours_clamped[vis], ri["clamped"][vis].bool())
+    for k in ("color", "depth", "norm", "alpha"):
+        assert (ours[k] - ref[k]).abs().max().item() <= IMG_ATOL, k
+    del oi
+    cot = [torch.from_numpy(c).to(dev) for c in S.cotangents(W, H, seed=1)]      # bench.py's cotangents
+    gb = Hh.run_ours_backward(d, cam, scene.sh_degree, bg_t, ours, cot)
+    r1 = [Hh.run_ref_backward(d, cam, scene.sh_degree, bg_t, ref, cot) for _ in range(3)]
+    Hh.adjudicate_gradients(d, cam, scene.sh_degree, bg_t, ri, ref["alpha"], ref["radii"], cot, gb, r1, name)
+    inv = ours["radii"] == 0
+    for k in ("means2D", "opacity", "means3D", "sh", "scales", "rot"):
+        assert gb[k][inv].abs().max().item() == 0.0, k       # culled Gaussians get exact zeros
+
+
+def test_long_thin_splats_crossing_many_tiles(cuda_device):
+    """Needle-shaped splats (axis ratio up to 1:1000) hundreds of pixels long: the quadratic form of the conic
+    cancels heavily far from the centre, which is where a block-level reach test could disagree with the reference's
+    per-pixel `alpha < 1/255` test.  Indexing incl. n_contrib bit for bit, images 1e-5, gradients adjudicated."""
+    if not ref_available():
+        pytest.skip("oracle/_ref not built")
+    from oracle import ref_cuda
+    dev = cuda_device
+    rng = np.random.default_rng(7)
+    scene = S.blob_scene(4000, seed=91, spread=2.0, scale=0.02)
+    scene.scales[:, 0] = np.exp(rng.uniform(np.log(0.5), np.log(8.0), scene.P)).astype(np.float32)    # long axis
+    scene.scales[:, 1] = np.exp(rng.uniform(np.log(0.002), np.log(0.02), scene.P)).astype(np.float32)  # needle
+    scene.scales[:, 2] = scene.scales[:, 1]
+    scene.opacities[:] = rng.uniform(0.004, 1.0, (scene.P, 1)).astype(np.float32)   # includes values near 1/255
+    scene.opacities[::97] = np.float32(1.0) / np.float32(255.0)                      # exactly the threshold
+    cam = S.simple_camera(640, 400, fov_deg=50.0, distance=9.0)
+    for ks in (0.1, 0.0005):      # the second filter size leaves the conic nearly singular
+        d, bg_t, col, ours, ref = run_pair(scene, cam, dev, bg=(0.2, 0.1, 0.0), kernel_size=ks)
+        P, H, W = scene.P, cam.height, cam.width
+        oi, ri = Hh.our_internals(ours, P, H, W), ref_cuda.internals(ref, P, H, W)
+        assert torch.equal(oi["point_list"], ri["point_list"]) and torch.equal(oi["ranges"], ri["ranges"])
+        assert torch.equal(oi["n_contrib"], ri["n_contrib"]), f"n_contrib differs (kernel_size {ks})"
+        for k in ("color", "depth", "norm", "alpha"):
+            assert (ours[k] - ref[k]).abs().max().item() <= IMG_ATOL, (k, ks)
+        cot = [torch.from_numpy(c).to(dev) for c in S.cotangents(W, H, seed=12)]
+        gb = Hh.run_ours_backward(d, cam, 3, bg_t, ours, cot, kernel_size=ks)
+        r1 = [Hh.run_ref_backward(d, cam, 3, bg_t, ref, cot, kernel_size=ks) for _ in range(3)]
+        Hh.adjudicate_gradients(d, cam, 3, bg_t, ri, ref["alpha"], ref["radii"], cot, gb, r1, f"needles[k={ks}]",
+                                kernel_size=ks)

@@ -73,3 +73,29 @@ def test_dist_cuda2_matches_bruteforce_and_reference(cuda_device):
         pts = torch.from_numpy(clouds["uniform"].astype(np.float32)).to(dev)
         # same 3-NN set; the squared distance may contract differently (1 ulp)
         assert torch.allclose(distCUDA2(pts), ref_cuda.knn(pts), rtol=1e-6, atol=0)
+
+
+def test_expf_replica_is_bit_exact(cuda_device):
+    """The blend kernels evaluate expf through a hand-scheduled replica of the compiler's routine (constants pinned in
+    registers, csrc/sfgs_common.cuh).  The alpha thresholds that decide n_contrib sit on its result, so it must equal
+    expf() bit for bit: a dense sweep of the range the kernels use, every exponent/sign pattern, and special values."""
+    from sfgs import native as N
+    dev = cuda_device
+    g = torch.Generator(device="cpu").manual_seed(3)
+    parts = [torch.linspace(-110.0, 0.0, 8_000_001, dtype=torch.float64).float(),          # the kernels' range
+             -torch.rand(4_000_000, generator=g).mul(20.0),                                 # where alpha is decided
+             -torch.exp(torch.rand(2_000_000, generator=g) * 60.0 - 50.0),                  # log-uniform magnitudes
+             torch.randint(-2 ** 31, 2 ** 31 - 1, (4_000_000,), generator=g, dtype=torch.int64).to(torch.int32).view(torch.float32),
+             torch.tensor([0.0, -0.0, 1.0, -1.0, 88.7, 88.8, -87.3, -87.4, -103.9, -104.1, float("inf"), float("-inf"),
+                           1e-45, -1e-45, 1.1754944e-38, -1.1754944e-38, 3.0e38, -3.0e38])]
+    x = torch.cat(parts).to(dev)
+    yr, ye = torch.empty_like(x), torch.empty_like(x)
+    N.check(N.lib().sfgs_selftest_expf(x.numel(), x.data_ptr(), yr.data_ptr(), ye.data_ptr(),
+                                       torch.cuda.current_stream(dev).cuda_stream), "selftest_expf")
+    torch.cuda.synchronize(dev)
+    ok = (yr.view(torch.int32) == ye.view(torch.int32)) | (torch.isnan(yr) & torch.isnan(ye))
+    # the kernels only ever use the value for arguments <= 0 (a positive `power` is rejected before/independently)
+    neg = x <= 0
+    bad = (~ok) & neg
+    assert int(bad.sum()) == 0, f"{int(bad.sum())} mismatches for x <= 0, e.g. x = {x[bad][:5].tolist()}"
+    assert float(ok.float().mean()) > 0.999, "replica should agree with expf on (almost) every bit pattern"
