@@ -21,11 +21,24 @@ Printed (rank 0, ONE JSON line):
            / its mean launch duration measured live with CUDA events around the launch.
   cpu_baseline  the CPU oracle (oracle/sfgs_oracle.c, a port: the reference has no CPU
            path) timed on this box's host cores on a bounded sample.
-`--impl reference` times the UNMODIFIED reference CUDA rasterizer (oracle/_ref, built from
-/root/reference's own sources) the same two ways; if that library is absent it falls back
-to the CPU oracle port.  Multi-GPU: ranks render different cameras of the replicated scene
-(weak scaling, no data-path collective); `--shard tilerows` splits ONE frame by tile rows
-and all-gathers the image with NCCL (strong scaling, BASELINE configs[3] style).
+`--impl reference` times the UNMODIFIED reference through its own stock code path: its pybind module `diff_gauss._C`
+(RAST/ext.cpp, rasterize_points.cu, cuda_rasterizer/*.cu) for `value` and its own autograd wrapper
+`diff_gauss.GaussianRasterizer` for `e2e`, installed into oracle/_ref by oracle/build_ref_torch.py; if that install is
+absent it falls back to the reference core behind the ctypes shim (oracle/_ref/libref_rasterizer.so), and to the CPU
+oracle port if nothing was built.  `reference_kind` in the line says which.
+
+Extra records in the same line (single-GPU run only; they never change `value`):
+  extra_frames  the SURVEY 8d whole-scene orbit camera, the BASELINE configs[3] 5M-Gaussian scene and its dense variant:
+                Mpix/s, V, R and (this library) per-stage times, device-resident leg;
+  ssim          fused-ssim forward(train)+backward at 1x3x1080x1920 with the 72N / 84N-byte roofline of SURVEY 8d, this
+                library next to the reference's compiled kernel (when oracle/_ref has it);
+  roofline.traffic  dram__bytes_read + dram__bytes_write of the dominant kernel measured in THIS run by an `ncu`
+                subprocess (falls back to profiles/traffic.json and says so in `traffic_source`).
+Multi-GPU: the headline is the "views" mode — ranks render different cameras of the replicated scene (weak scaling, no
+data-path collective).  In the same invocation every rank then also runs the tile-row sharded mode (ONE frame split by
+balanced bands of tile rows, image all-gather and [P,16] reduce-scatter fused into the kernels over NVLink peer memory,
+sfgs/multigpu.py) on the 1M scene and on BASELINE configs[3] (5M Gaussians); those strong-scaling records are attached
+as `tilerows`.  `--shard tilerows` prints only that mode.
 """
 from __future__ import annotations
 
@@ -149,6 +162,7 @@ def make_inputs(scene, cam, dev):
              projmatrix=t(cam.projmatrix), campos=t(cam.campos), bg=torch.zeros(3, device=dev))
     d["cot"] = [t(c) for c in S.cotangents(cam.width, cam.height, seed=1)]
     d["empty"] = torch.empty(0, device=dev)
+    d["cpu_empty"] = torch.Tensor([])
     return d
 
 
@@ -178,6 +192,42 @@ def step_ref(d, cam):
                           d["shs"], SH_DEGREE, d["campos"], f["geom"], f["num_rendered"], f["binning"], f["img"],
                           f["alpha"])
     return f, g
+
+
+_REF_PKGS = None
+
+
+def ref_packages():
+    """(ref_diff_gauss, ref_fused_ssim): the reference's own packages as installed by oracle/build_ref_torch.py."""
+    global _REF_PKGS
+    if _REF_PKGS is None:
+        from oracle import build_ref_torch
+        _REF_PKGS = build_ref_torch.import_reference_packages()
+    return _REF_PKGS
+
+
+def reference_kind():
+    from oracle import build_ref_torch, ref_cuda
+    if build_ref_torch.built():
+        return "stock"
+    return "shim" if ref_cuda.available() else "cpu"
+
+
+def step_ref_stock(d, cam):
+    """The reference's own pybind entry points, called the way its diff_gauss/__init__.py calls them (positional
+    orders of RAST/rasterize_points.h:17-73; `None` arguments arrive as empty CPU tensors there)."""
+    C_ = ref_packages()[0]._C
+    e = d["cpu_empty"]
+    f = C_.rasterize_gaussians(d["bg"], d["means3D"], e, d["opacities"], d["scales"], d["rotations"], 1.0, e, e, e, 0,
+                               d["viewmatrix"], d["projmatrix"], cam.tanfovx, cam.tanfovy, 0.1, cam.height, cam.width,
+                               d["shs"], SH_DEGREE, d["campos"], False, False)
+    num_rendered, color, depth, norm, alpha, radii, extra, geom, binning, img = f
+    c = d["cot"]
+    g = C_.rasterize_gaussians_backward(d["bg"], d["means3D"], radii, e, d["scales"], d["rotations"], e, 1.0, e, e,
+                                        d["viewmatrix"], d["projmatrix"], cam.tanfovx, cam.tanfovy, 0.1, c[0], c[1], c[2],
+                                        c[3], e, d["shs"], SH_DEGREE, d["campos"], geom, num_rendered, binning, img, alpha,
+                                        False)
+    return (num_rendered, color, depth, norm, alpha, radii), g
 
 
 def timed_steps(step_fn, steps, warmup, flush, dev, between=None):
@@ -227,12 +277,12 @@ def measure(step_fn, steps, warmup, flush, dev, between=None, max_attempts=5):
 
 
 # ----------------------------------------------------------------------------- public-API leg ("e2e")
-class E2EOurs:
-    """render -> L1-style loss -> backward through diff_gauss, with per-step H2D of camera + target image."""
+class E2E:
+    """render -> L1-style loss -> backward through a `diff_gauss` package (this library's drop-in, or the reference's
+    own package), with per-step H2D of camera + target image and a D2H read of the loss."""
 
-    def __init__(self, scene, cam, dev):
-        from diff_gauss import GaussianRasterizationSettings, GaussianRasterizer
-        self.GRS, self.GR = GaussianRasterizationSettings, GaussianRasterizer
+    def __init__(self, scene, cam, dev, pkg):
+        self.GRS, self.GR = pkg.GaussianRasterizationSettings, pkg.GaussianRasterizer
         t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)  # noqa: E731
         self.dev, self.cam = dev, cam
         self.params = [t(scene.means3D).requires_grad_(True), t(scene.opacities).requires_grad_(True),
@@ -274,20 +324,17 @@ class E2EOurs:
         self.h_loss.copy_(loss.detach().reshape(1), non_blocking=True)
 
 
-class E2ERef:
-    """The same step through the unmodified reference CUDA rasterizer (no autograd wrapper: gradients of the
-    same loss are formed by hand and fed to its backward)."""
+class E2ERefShim:
+    """Fallback when the reference's own torch extension was not installed: the reference CUDA core behind the ctypes
+    shim (no autograd wrapper: gradients of the same loss are formed by hand and fed to its backward)."""
 
     def __init__(self, scene, cam, dev):
         self.d = make_inputs(scene, cam, dev)
         self.dev, self.cam = dev, cam
         rng = np.random.default_rng(5)
         self.h_cam = torch.from_numpy(np.concatenate([cam.viewmatrix.ravel(), cam.projmatrix.ravel(), cam.campos])).pin_memory()
-        # the target image travels as 8-bit RGB, the way image datasets are stored, and is converted on the device
         self.h_gt = torch.from_numpy(rng.integers(0, 256, size=(3, cam.height, cam.width), dtype=np.uint8)).pin_memory()
         self.h_loss = torch.zeros(1).pin_memory()
-        self.h2d_bytes = self.h_cam.numel() * 4 + self.h_gt.numel()
-        self.d2h_bytes = 4
         self.copy_stream = torch.cuda.Stream(dev)
 
     def step(self):
@@ -303,7 +350,7 @@ class E2ERef:
                              proj, cam.tanfovx, cam.tanfovy, 0.1, cam.height, cam.width, d["shs"], SH_DEGREE, campos)
         cur.wait_stream(self.copy_stream)
         gt.record_stream(cur)
-        gt = torch.mul(gt, 1.0 / 255.0)          # uint8 -> float32 in [0,1], one kernel
+        gt = torch.mul(gt, 1.0 / 255.0)
         n = float(cam.height * cam.width)
         norm_raw = f["norm"].detach().requires_grad_(True)
         norm = torch.nn.functional.normalize(norm_raw, p=2, dim=0)
@@ -340,6 +387,126 @@ def cpu_baseline(scene, cam, max_seconds=25.0):
                       f"best of {len(times)}, OpenMP over {O.num_threads()} threads"}
 
 
+# ----------------------------------------------------------------------------- extra records (N = 1 only)
+EXTRA_FRAMES = {
+    # name: (P, extent, camera)   — the same (scene, camera) pairs tests/test_gpu_parity.py diffs against the reference
+    "configs1_1M_orbit": (1_000_000, 256.0, "orbit"),      # whole scene in view, fov 60, radius 300, elevation 85
+    "configs3_5M_jax004": (5_000_000, 256.0 * 5 ** 0.5, "jax"),   # BASELINE configs[3]: same generator, extent x sqrt(5)
+    "dense_5M_jax004": (5_000_000, 256.0, "jax"),          # 5x the density in the same extent: long tile lists
+}
+
+
+def frame_record(name, impl_kind, dev, steps):
+    """Device-resident fwd+bwd of one extra frame: Mpix/s (median step), V, R and, for this library, stage times."""
+    from sfgs import native
+    P, extent, camname = EXTRA_FRAMES[name]
+    scene = S.city_scene(P, seed=0, sh_degree=SH_DEGREE, extent=extent)
+    cam = S.jax004_camera(W_IMG, H_IMG) if camname == "jax" else S.orbit_camera(width=W_IMG, height=H_IMG)
+    d = make_inputs(scene, cam, dev)
+    flush = L2Flusher(dev)
+    step = {"ours": lambda: step_ours(d, cam), "stock": lambda: step_ref_stock(d, cam), "shim": lambda: step_ref(d, cam)}[impl_kind]
+    ms = timed_steps(step, steps, 3, flush, dev)
+    med = float(np.median(ms))
+    f, _ = step()
+    torch.cuda.synchronize(dev)
+    if impl_kind == "shim":
+        R, radii = int(f["num_rendered"]), f["radii"]
+    else:
+        R, radii = int(f[0]), f[5]
+    rec = {"name": name, "P": P, "extent": round(extent, 2), "camera": camname, "value": round(cam.width * cam.height / med / 1e3, 2),
+           "unit": "Mpix/s", "ms_per_step": round(med, 4), "ms_min": round(min(ms), 4), "steps": steps,
+           "V": int((radii > 0).sum().item()), "R": R}
+    if impl_kind == "ours":
+        per_stage = {}
+        for _ in range(5):
+            flush()
+            native.profile_enable(True)
+            step()
+            torch.cuda.synchronize(dev)
+            for k, v in native.profile_read().items():
+                per_stage.setdefault(k, []).append(v[0] / v[1] if v[1] else 0.0)
+        native.profile_enable(False)
+        rec["stages_ms"] = {k: round(float(np.median(v)), 4) for k, v in per_stage.items()}
+    del d, scene
+    torch.cuda.empty_cache()
+    return rec
+
+
+def ssim_record(impl_kind, dev, steps=20):
+    """fused-ssim forward(train) and backward at the training shape [1,3,1080,1920]; bytes per SURVEY 8d:
+    forward reads 2 and writes 4 planes (72*N bytes at 3 channels), backward reads 6 and writes 1 (84*N)."""
+    if impl_kind == "ours":
+        import fused_ssim as fs
+    elif impl_kind == "stock":
+        fs = ref_packages()[1]
+    else:
+        return None
+    H, W, C = H_IMG, W_IMG, 3
+    g = torch.Generator(device="cpu").manual_seed(2)
+    a = torch.rand((1, C, H, W), generator=g).to(dev)
+    b = (a + 0.1 * torch.randn((1, C, H, W), generator=g).to(dev)).clamp(0, 1)
+    dL = torch.full((1, C, H, W), 1.0 / (C * H * W), device=dev)
+    flush = L2Flusher(dev)
+    C1, C2 = 0.01 ** 2, 0.03 ** 2
+    t_f, t_b = [], []
+    for i in range(steps + 3):
+        flush()
+        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        e0.record()
+        m, d1, d2, d3 = fs.fusedssim(C1, C2, a, b, True)
+        e1.record()
+        gimg = fs.fusedssim_backward(C1, C2, a, b, dL, d1, d2, d3)
+        e2.record()
+        torch.cuda.synchronize(dev)
+        if i >= 3:
+            t_f.append(e0.elapsed_time(e1)); t_b.append(e1.elapsed_time(e2))
+    N = H * W
+    peak, _ = peaks()
+    mf, mb = float(np.median(t_f)), float(np.median(t_b))
+    return {"shape": [1, C, H, W], "fwd_ms": round(mf, 4), "bwd_ms": round(mb, 4),
+            "fwd_algorithmic_bytes": 24 * C * N, "bwd_algorithmic_bytes": 28 * C * N,
+            "fwd_GBps": round(24 * C * N / mf / 1e6, 1), "bwd_GBps": round(28 * C * N / mb / 1e6, 1),
+            "fwd_frac_of_hbm_peak": round(24 * C * N / mf / 1e6 / peak, 4), "bwd_frac_of_hbm_peak": round(28 * C * N / mb / 1e6 / peak, 4),
+            "timing": "CUDA events around each call (includes the output allocations of the op), L2 flushed, median",
+            "mean_ssim": round(float(m.mean().item()), 6), "grad_abs_max": float(gimg.abs().max().item())}
+
+
+def live_traffic(kernel_regex, timeout_s=240):
+    """dram__bytes_read + dram__bytes_write (and issue-slot utilisation) of ONE launch of the dominant kernel, captured in
+    this run by an ncu subprocess over tests/gpu_profile_case.py (same scene, camera and cotangents as the timed loop).
+    Returns None when ncu is unavailable."""
+    import csv
+    import shutil
+    import tempfile
+    ncu = shutil.which("ncu") or "/usr/local/cuda/bin/ncu"
+    if not os.path.exists(ncu):
+        return None
+    with tempfile.TemporaryDirectory() as td:
+        log = os.path.join(td, "t.csv")
+        cmd = [ncu, "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum,sm__issue_active.avg.pct_of_peak_sustained_elapsed,"
+               "smsp__inst_executed.sum,gpu__time_duration.sum", "--clock-control", "none", "-k", f"regex:{kernel_regex}",
+               "-s", "1", "-c", "1", "--csv", "--log-file", log, sys.executable, os.path.join(ROOT, "tests", "gpu_profile_case.py"),
+               "--iters", "2"]
+        try:
+            subprocess.run(cmd, capture_output=True, text=True, timeout=timeout_s, check=True)
+            vals = {}
+            with open(log) as fh:
+                rows = [r for r in csv.reader(l for l in fh if not l.startswith("=="))]
+            hdr = rows[0]
+            for r in rows[1:]:
+                row = dict(zip(hdr, r))
+                v = float(row["Metric Value"].replace(",", ""))
+                unit = row.get("Metric Unit", "")
+                scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1)
+                vals[row["Metric Name"]] = v * scale
+            return {"traffic": int(vals["dram__bytes_read.sum"] + vals["dram__bytes_write.sum"]),
+                    "issue_active_pct": round(vals["sm__issue_active.avg.pct_of_peak_sustained_elapsed"], 1),
+                    "warp_instructions": int(vals["smsp__inst_executed.sum"])}
+        except Exception as exc:  # noqa: BLE001
+            print(f"[bench] live ncu capture failed: {type(exc).__name__}: {str(exc)[:200]}", file=sys.stderr)
+            return None
+
+
 # ----------------------------------------------------------------------------- main
 def main():
     ap = argparse.ArgumentParser()
@@ -350,7 +517,8 @@ def main():
     ap.add_argument("--shard", default="views", choices=["views", "tilerows"])
     ap.add_argument("--P", type=int, default=P_GAUSS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-clocks", action="store_true", help="do not poll nvidia-smi during the timed region")
+    ap.add_argument("--no-clocks", action="store_true", help="do not sample SM clocks during the timed region")
+    ap.add_argument("--no-extras", action="store_true", help="skip the extra frames / ssim / ncu / tile-row records")
     args = ap.parse_args()
     steps, warmup = max(1, args.steps), max(3, args.warmup)
 
@@ -363,9 +531,8 @@ def main():
     dev = torch.device(f"cuda:{local_rank}")
     torch.cuda.set_device(dev)
 
-    from oracle import ref_cuda
-    use_ref_cuda = args.impl == "reference" and ref_cuda.available()
-    if args.impl == "reference" and not use_ref_cuda:
+    kind = "ours" if args.impl == "ours" else reference_kind()
+    if kind == "cpu":
         return reference_cpu_arm(args, rank, world, steps, warmup)
 
     if args.shard == "tilerows" and world > 1 and args.impl == "ours":
@@ -379,9 +546,11 @@ def main():
     flush = L2Flusher(dev)
 
     from sfgs import native
-    if args.impl == "ours":
+    if kind == "ours":
         native.lib()
         step = lambda: step_ours(d, cam)  # noqa: E731
+    elif kind == "stock":
+        step = lambda: step_ref_stock(d, cam)  # noqa: E731
     else:
         step = lambda: step_ref(d, cam)   # noqa: E731
 
@@ -401,7 +570,13 @@ def main():
     value = world * steps * N / (total_ms / 1e3) / 1e6
 
     # ---- e2e: public API with host<->device copies inside the timed region
-    e2e_obj = (E2EOurs if args.impl == "ours" else E2ERef)(scene, cam, dev)
+    if kind == "ours":
+        import diff_gauss as pkg
+        e2e_obj = E2E(scene, cam, dev, pkg)
+    elif kind == "stock":
+        e2e_obj = E2E(scene, cam, dev, ref_packages()[0])
+    else:
+        e2e_obj = E2ERefShim(scene, cam, dev)
     e2e_ms, e2e_info = measure(e2e_obj.step, steps, warmup, flush, dev)
     e2e_total = torch.tensor([sum(e2e_ms)], dtype=torch.float64, device=dev)
     if world > 1:
@@ -409,12 +584,30 @@ def main():
     e2e_value = world * steps * N / (float(e2e_total.item()) / 1e3) / 1e6
     del e2e_obj
 
+    # ---- tile-row sharded mode, same invocation (every rank takes part; strong scaling; SURVEY 8e / BASELINE configs[3])
+    tilerows = None
+    if world > 1 and kind == "ours" and not args.no_extras:
+        from sfgs import multigpu
+        del d
+        torch.cuda.empty_cache()
+        tilerows = []
+        for label, P_t, extent in (("1M", P_GAUSS, 256.0), ("configs3_5M", 5_000_000, 256.0 * 5 ** 0.5), ("dense_5M", 5_000_000, 256.0)):
+            try:
+                tsamp = ClockSampler(local_rank, dev)
+                rec = multigpu.run_tilerows(P_t, extent, rank, world, dev, max(10, steps), warmup)
+                tsamp.sample()
+                rec["clocks"] = tsamp.stop()
+                rec["label"] = label
+                tilerows.append(rec)
+            except Exception as exc:  # noqa: BLE001
+                tilerows.append({"label": label, "error": f"{type(exc).__name__}: {exc}"[:300]})
+        d = make_inputs(scene, cam, dev)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    # ---- stage profile + roofline (rank 0, ours only)
     out = {"metric": METRIC, "value": round(value, 2), "unit": "Mpix/s", "n_gpus": world, "steps": steps,
            "warmup": warmup, "ms_per_step": round(total_ms / steps, 4), "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -428,9 +621,12 @@ def main():
            "clocks": clocks}
     out["timing"] = {"value": value_info, "e2e": e2e_info,
                      "rule": "a pass whose mean step exceeds 1.05x its fastest step is re-measured (<= 5 passes)"}
-    out["e2e"]["api"] = ("diff_gauss.GaussianRasterizer + autograd" if args.impl == "ours"
-                         else "reference CudaRasterizer::Rasterizer forward/backward")
-    if args.impl == "ours":
+    out["e2e"]["api"] = {"ours": "diff_gauss.GaussianRasterizer + autograd (this library's drop-in package)",
+                         "stock": "the reference's own diff_gauss.GaussianRasterizer + autograd over its own pybind module",
+                         "shim": "reference CudaRasterizer::Rasterizer forward/backward behind the ctypes shim"}[kind]
+    if tilerows is not None:
+        out["tilerows"] = tilerows
+    if kind == "ours":
         l0 = native.lib().sfgs_launch_count()
         f, _ = step()
         torch.cuda.synchronize(dev)
@@ -457,21 +653,10 @@ def main():
         ach = alg[dom] / (stage_ms[dom] / 1e3) / 1e9
         b_total = sum(alg.values())
         t_kernels = sum(stage_ms.values())
-        traffic, issue = None, None
-        tpath = os.path.join(ROOT, "profiles", "traffic.json")   # dram__bytes_read+write per launch from `ncu --set full`
-        if os.path.exists(tpath):
-            with open(tpath) as f:
-                tj = json.load(f)
-            traffic = tj.get("kernels", {}).get(dom)
-            issue = tj.get("issue_slots_active_pct", {}).get(dom)
         out["roofline"] = {"bound": "hbm", "kernel": dom, "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
-                           "frac": round(ach / peak, 4), "traffic": traffic, "peak_source": peak_src,
+                           "frac": round(ach / peak, 4), "traffic": None, "peak_source": peak_src,
                            "algorithmic_bytes": int(alg[dom]), "kernel_ms": round(stage_ms[dom], 4),
                            "share_of_step": round(stage_ms[dom] / t_kernels, 3)}
-        if issue is not None:
-            # the blend kernels are bound by instruction issue, not by HBM: say so next to the HBM fraction
-            out["roofline"]["limiter"] = (f"instruction issue: {issue}% of issue slots active (ncu, "
-                                          "profiles/r1e_all_kernels_full.md); DRAM traffic is the `traffic` field")
         out["roofline_pipeline"] = {"algorithmic_bytes": int(b_total), "kernels_ms": round(t_kernels, 4),
                                     "achieved": round(b_total / (t_kernels / 1e3) / 1e9, 1), "unit": "GB/s",
                                     "frac": round(b_total / (t_kernels / 1e3) / 1e9 / peak, 4)}
@@ -479,8 +664,41 @@ def main():
         out["counts"] = {"P": scene.P, "V": V, "R": R, "N": N}
     else:
         out["impl"] = "reference"
-        out["reference_kind"] = "unmodified reference CUDA rasterizer (oracle/_ref), same GPU, same inputs"
-        out["e2e"]["note"] = "same host<->device copies as the product arm"
+        out["reference_kind"] = {"stock": "unmodified reference through its own pybind module and autograd wrapper (oracle/_ref, "
+                                          "installed by oracle/build_ref_torch.py), same GPU, same inputs",
+                                 "shim": "unmodified reference CUDA core behind a ctypes shim (oracle/_ref/libref_rasterizer.so)"}[kind]
+        out["e2e"]["note"] = "same host<->device copies and the same loss code as the product arm"
+
+    # ---- extra records: other frames, fused-ssim, live DRAM traffic (single-GPU run only)
+    if world == 1 and not args.no_extras:
+        del d
+        torch.cuda.empty_cache()
+        frames = []
+        for name in EXTRA_FRAMES:
+            try:
+                frames.append(frame_record(name, kind, dev, max(10, steps // 2)))
+            except Exception as exc:  # noqa: BLE001
+                frames.append({"name": name, "error": f"{type(exc).__name__}: {exc}"[:300]})
+        out["extra_frames"] = frames
+        try:
+            out["ssim"] = ssim_record(kind, dev)
+        except Exception as exc:  # noqa: BLE001
+            out["ssim"] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+        if kind == "ours":
+            torch.cuda.synchronize(dev)
+            lt = live_traffic({"render_bwd": "render_bwd_kernel", "render_fwd": "render_fwd_kernel"}.get(dom, dom))
+            if lt is not None:
+                out["roofline"].update(traffic=lt["traffic"], traffic_source="ncu subprocess in this run (one launch, "
+                                       "dram__bytes_read.sum + dram__bytes_write.sum)")
+                out["roofline"]["limiter"] = (f"instruction issue: {lt['issue_active_pct']}% of issue slots active, "
+                                              f"{lt['warp_instructions']} warp instructions (same ncu capture)")
+            else:
+                tpath = os.path.join(ROOT, "profiles", "traffic.json")
+                if os.path.exists(tpath):
+                    with open(tpath) as fh:
+                        tj = json.load(fh)
+                    out["roofline"].update(traffic=tj.get("kernels", {}).get(dom),
+                                           traffic_source="profiles/traffic.json (committed ncu capture; live capture unavailable)")
     if not args.no_cpu_baseline and world == 1:   # the CPU port is timed on rank 0 of the single-GPU run only
         out["cpu_baseline"] = cpu_baseline(scene, cam)
     print(json.dumps(out))

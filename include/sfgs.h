@@ -219,6 +219,10 @@ int sfgs_image_layout(char* base, int width, int height, sfgs_image_view* out);
 int sfgs_binning_layout(char* base, long long capacity, sfgs_binning_view* out);
 /* capacity (in tile instances) the last forward on this buffer was sized for; stored in the image buffer header */
 long long sfgs_last_capacity(void);
+/* how many forwards since load had to run twice because the binning buffer estimate was too small.  The estimate is
+ * kept per (device, P, width, height, tile-row band), so alternating frame sizes of one scene costs one re-run per new
+ * size at most, not one per switch. */
+long long sfgs_overflow_reruns(void);
 
 /* ---- fused per-Gaussian activations ------------------
  * The torch pre-ops of every render() call as one kernel each way:

@@ -69,6 +69,7 @@ __global__ void expf_selftest_kernel(int n, const float* __restrict__ x, float* 
 
 thread_local char t_err[512] = "";
 std::atomic<long long> g_last_capacity{0};
+std::atomic<long long> g_overflow_reruns{0};   // forwards that had to run twice because the binning estimate was too small
 
 // Running estimate of the instance count, keyed by what determines it to first order: (device, P, image size, band).
 // A training loop alternates 1080p train views, 1024^2 pseudo-views and low-resolution evaluation renders of the
@@ -181,10 +182,14 @@ thread_local PinnedHdr t_hdr_dev[MAX_DEVICES];
 
 extern "C" {
 
+// error entry for the other translation units (SSIM, KNN): same thread-local text as the rasterizer's
+int sfgs_set_error(int code, const char* what, int cuda_error) { return fail(code, what, (cudaError_t)cuda_error); }
+
 const char* sfgs_last_error(void) { return t_err; }
 int sfgs_version(void) { return SFGS_VERSION; }
 long long sfgs_launch_count(void) { return g_sfgs_launches.load(); }
 long long sfgs_last_capacity(void) { return g_last_capacity.load(); }
+long long sfgs_overflow_reruns(void) { return g_overflow_reruns.load(); }
 
 size_t sfgs_geom_bytes(int P) { return GeomLayout(nullptr, (size_t)(P > 0 ? P : 0)).bytes; }
 size_t sfgs_image_bytes(int width, int height) { return ImageLayout(nullptr, width, height).bytes; }
@@ -310,6 +315,7 @@ int sfgs_rasterize_forward(const sfgs_forward_args* a) {
     if (!hhdr[HDR_OVERFLOW]) break;
     if (attempt == 2) return fail(SFGS_E_CUDA, "forward: binning capacity overflow persisted");
     capacity = R + R / 16 + 4096;   // the exact count is now known; run the pipeline again with room for it
+    g_overflow_reruns.fetch_add(1);
   }
   cap_store(cap_key, R);
   g_last_capacity.store(capacity);

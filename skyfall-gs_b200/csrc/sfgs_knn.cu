@@ -214,11 +214,13 @@ knn_query_kernel(int P, const KnnParams* __restrict__ prm, const uint32_t* __res
 
 }  // namespace
 
+extern "C" int sfgs_set_error(int code, const char* what, int cuda_error);   // sfgs_api.cu
+
 extern "C" int sfgs_dist2_knn3(int P, const float* points, float* mean_dist2, sfgs_alloc_fn scratch_alloc,
                                void* scratch_user, void* stream) {
-  if (P < 0) return SFGS_E_BADARG;
+  if (P < 0) return sfgs_set_error(SFGS_E_BADARG, "dist2_knn3: P < 0", 0);
   if (P == 0) return SFGS_OK;
-  if (!points || !mean_dist2 || !scratch_alloc) return SFGS_E_BADARG;
+  if (!points || !mean_dist2 || !scratch_alloc) return sfgs_set_error(SFGS_E_BADARG, "dist2_knn3: null pointer", 0);
   cudaStream_t st = (cudaStream_t)stream;
   unsigned long long cap = (unsigned long long)P * 2ull;
   if (cap < 4096ull) cap = 4096ull;
@@ -231,7 +233,7 @@ extern "C" int sfgs_dist2_knn3(int P, const float* points, float* mean_dist2, sf
   const size_t o_cursor = carve(((size_t)cell_cap + 1) * 4), o_cop = carve((size_t)P * 4);
   const size_t o_sorted = carve((size_t)P * sizeof(float4));
   char* raw = scratch_alloc(scratch_user, off + SFGS_ALIGN);
-  if (!raw) return SFGS_E_ALLOC;
+  if (!raw) return sfgs_set_error(SFGS_E_ALLOC, "dist2_knn3: scratch allocator returned NULL", 0);
   char* base = sfgs_align_ptr(raw);
   int* bbox = (int*)(base + o_bbox);
   KnnParams* prm = (KnnParams*)(base + o_prm);
@@ -241,7 +243,8 @@ extern "C" int sfgs_dist2_knn3(int P, const float* points, float* mean_dist2, sf
   uint32_t* cop = (uint32_t*)(base + o_cop);
   float4* sorted = (float4*)(base + o_sorted);
 
-  if (cudaMemsetAsync(cell_count, 0, ((size_t)cell_cap + 1) * 4, st) != cudaSuccess) return SFGS_E_CUDA;
+  if (cudaMemsetAsync(cell_count, 0, ((size_t)cell_cap + 1) * 4, st) != cudaSuccess)
+    return sfgs_set_error(SFGS_E_CUDA, "dist2_knn3: memset", (int)cudaGetLastError());
   const int pb = (P + 255) / 256;
   SFGS_COUNT_LAUNCH(); knn_init_kernel<<<1, 32, 0, st>>>(bbox);
   SFGS_COUNT_LAUNCH(); knn_bbox_kernel<<<pb < 592 ? pb : 592, 256, 0, st>>>(P, points, bbox);
@@ -250,5 +253,6 @@ extern "C" int sfgs_dist2_knn3(int P, const float* points, float* mean_dist2, sf
   SFGS_COUNT_LAUNCH(); knn_scan_kernel<<<1, 1024, 0, st>>>(prm, cell_count, cell_start, cell_cursor);
   SFGS_COUNT_LAUNCH(); knn_fill_kernel<<<pb, 256, 0, st>>>(P, points, cop, cell_start, cell_cursor, sorted);
   SFGS_COUNT_LAUNCH(); knn_query_kernel<<<(P + 127) / 128, 128, 0, st>>>(P, prm, cell_start, sorted, mean_dist2);
-  return cudaGetLastError() == cudaSuccess ? SFGS_OK : SFGS_E_CUDA;
+  const cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? SFGS_OK : sfgs_set_error(SFGS_E_CUDA, "dist2_knn3", (int)e);
 }

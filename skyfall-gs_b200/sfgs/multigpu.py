@@ -133,13 +133,27 @@ def row_histogram(ranges: torch.Tensor, tiles_x: int) -> List[int]:
 
 # ----------------------------------------------------------------------------- bench leg (NCCL, one frame sharded)
 def bench_tilerows(args, rank, world, dev, steps, warmup, metric):
+    """`bench.py --shard tilerows`: one JSON line for the tile-row sharded frame (strong scaling)."""
     import json
+    rec = run_tilerows(args.P, 256.0, rank, world, dev, steps, warmup)
+    if rank == 0:
+        print(json.dumps({"metric": metric, "value": rec["value"], "unit": "Mpix/s", "n_gpus": world, "steps": steps,
+                          "warmup": warmup, "ms_per_step": rec["ms_per_step"], "higher_is_better": True,
+                          "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                          "config": {"workload": rec["workload"], "P": rec["P"], "parallelism": rec["parallelism"],
+                                     "cuts": rec["cuts"], "l2": "not flushed (collectives in the loop)"}}))
+    dist.destroy_process_group()
 
+
+def run_tilerows(P, extent, rank, world, dev, steps, warmup):
+    """Time `steps` forward+backward passes of ONE 1920x1080 frame of the `P`-Gaussian scene split by tile rows over the
+    ranks of the default process group (every rank must call this).  Returns a dict (identical on every rank):
+    value [Mpix/s], ms_per_step (device time, max over ranks), the exchange mechanisms used and the band cuts."""
     import numpy as np
 
     from . import rasterizer as R
     from . import synthetic as S
-    scene = S.city_scene(args.P, seed=0, sh_degree=3)
+    scene = S.city_scene(P, seed=0, sh_degree=3, extent=extent)
     cam = S.jax004_camera(1920, 1080)
     t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)  # noqa: E731
     d = dict(means3D=t(scene.means3D), scales=t(scene.scales), rotations=t(scene.rotations),
@@ -149,6 +163,8 @@ def bench_tilerows(args, rank, world, dev, steps, warmup, metric):
     e = torch.empty(0, device=dev)
     H, W = cam.height, cam.width
     rows, tiles_x = tile_rows(H), (W + TILE - 1) // TILE
+
+    last = {"R": 0}
 
     def fwd(band):
         return R.rasterize_gaussians(d["bg"], d["means3D"], e, d["opacities"], d["scales"], d["rotations"], 1.0, e, e,
@@ -179,6 +195,7 @@ def bench_tilerows(args, rank, world, dev, steps, warmup, metric):
 
     def step_nccl():
         f = fwd(band)
+        last["R"] = f[0]
         planes = torch.cat([f[1], f[2], f[4], f[3]], 0)            # colour, depth, alpha, normal: 8 planes
         full = gather_bands(planes, cuts, H)
         bwd(f, phase=1, acc=acc_buf[:scene.P])                      # blend adjoint of this band -> partial sums
@@ -211,6 +228,7 @@ def bench_tilerows(args, rank, world, dev, steps, warmup, metric):
                                           e, e, e, 0, d["view"], d["proj"], cam.tanfovx, cam.tanfovy, 0.1, H, W,
                                           d["shs"], 3, d["campos"], False, False, tile_rows=band,
                                           out_planes=frame_sym, out_peers=frame_peers)
+                last["R"] = f[0]
                 fh.barrier(channel=1)                               # every band has landed everywhere
                 full = frame_sym.view(8, H, W)
                 acc_sym.zero_()
@@ -254,15 +272,13 @@ def bench_tilerows(args, rank, world, dev, steps, warmup, metric):
     torch.cuda.synchronize(dev)
     ms = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    if rank == 0:
-        total = float(ms.item())
-        print(json.dumps({"metric": metric, "value": round(steps * H * W / (total / 1e3) / 1e6, 2), "unit": "Mpix/s",
-                          "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": round(total / steps, 4),
-                          "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
-                          "data": "synthetic",
-                          "config": {"workload": f"one 1920x1080 frame of the {scene.P}-Gaussian scene sharded by tile rows",
-                                     "P": scene.P,
-                                     "parallelism": f"tilerows x{world}: {gather} + {collective}; each rank "
-                                                    "finishes the gradients of P/N Gaussians",
-                                     "cuts": cuts, "l2": "not flushed (collectives in the loop)"}}))
-    dist.destroy_process_group()
+    total = float(ms.item())
+    R_band = torch.tensor([float(last["R"])], dtype=torch.float64, device=dev)
+    R_all = [torch.zeros_like(R_band) for _ in range(world)]
+    dist.all_gather(R_all, R_band)
+    return {"workload": f"one 1920x1080 frame of the {scene.P}-Gaussian scene (extent {extent:g}) sharded by tile rows",
+            "P": scene.P, "value": round(steps * H * W / (total / 1e3) / 1e6, 2), "ms_per_step": round(total / steps, 4),
+            "steps": steps, "warmup": warmup,
+            "parallelism": f"tilerows x{world}: {gather} + {collective}; each rank finishes the gradients of P/N Gaussians",
+            "gather": gather, "collective": collective, "cuts": cuts,
+            "instances_per_band": [int(x.item()) for x in R_all], "timing": "CUDA events around the whole loop, max over ranks"}

@@ -92,7 +92,7 @@ EXPORTS = [
     "sfgs_fusedssim_forward", "sfgs_fusedssim_backward", "sfgs_dist2_knn3",
     "sfgs_activations_forward", "sfgs_activations_backward",
     "sfgs_last_error", "sfgs_version", "sfgs_launch_count", "sfgs_profile_enable", "sfgs_profile_read", "sfgs_sizeof", "sfgs_sm_clock_probe",
-    "sfgs_selftest_expf",
+    "sfgs_selftest_expf", "sfgs_overflow_reruns",
 ]
 STAGE_NAMES = ["fwd_zero", "preprocess", "tile_scan", "emit_keys", "tile_sort", "render_fwd", "bwd_zero", "render_bwd",
                "gauss_bwd"]
@@ -123,6 +123,7 @@ def lib() -> C.CDLL:
     L.sfgs_image_layout.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(ImageView)]; L.sfgs_image_layout.restype = C.c_int
     L.sfgs_binning_layout.argtypes = [C.c_void_p, C.c_longlong, C.POINTER(BinningView)]; L.sfgs_binning_layout.restype = C.c_int
     L.sfgs_last_capacity.argtypes = []; L.sfgs_last_capacity.restype = C.c_longlong
+    L.sfgs_overflow_reruns.argtypes = []; L.sfgs_overflow_reruns.restype = C.c_longlong
     L.sfgs_fusedssim_forward.argtypes = [C.c_float, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                          C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.sfgs_fusedssim_forward.restype = C.c_int

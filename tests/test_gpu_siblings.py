@@ -99,3 +99,56 @@ def test_expf_replica_is_bit_exact(cuda_device):
     bad = (~ok) & neg
     assert int(bad.sum()) == 0, f"{int(bad.sum())} mismatches for x <= 0, e.g. x = {x[bad][:5].tolist()}"
     assert float(ok.float().mean()) > 0.999, "replica should agree with expf on (almost) every bit pattern"
+
+
+def _ref_fused_ssim():
+    from oracle import build_ref_torch
+    if not build_ref_torch.built():
+        pytest.skip("oracle/_ref torch extensions not built")
+    return build_ref_torch.import_reference_packages()[1]
+
+
+@pytest.mark.parametrize("shape", [(5, 5, 1080, 1920), (1, 3, 1080, 1920), (2, 3, 270, 333), (1, 1, 17, 19), (1, 2, 64, 4),
+                                   (1, 3, 33, 130)])
+def test_fused_ssim_against_the_reference_cuda_kernel(cuda_device, shape):
+    """The reference's own compiled fused-ssim (SSIM/ssim.cu, built by oracle/build_ref_torch.py with its setup.py's
+    flags) as the oracle, first on its own test workload (SSIM/tests/test.py:81-83: B=5, CH=5, 1080x1920), then on
+    the training shape and on sizes that are off the tile grid, odd, narrower than a tile or not 16-byte rows (the
+    non-TMA load path).  The reference kernel is compiled with --use_fast_math (approximate divisions), so the
+    bar is its own accuracy: the map within 2e-6, the gradient within 1e-6 of its largest element."""
+    ref = _ref_fused_ssim()
+    from fused_ssim import fused_ssim, fusedssim, fusedssim_backward
+    dev = cuda_device
+    g = torch.Generator(device="cpu").manual_seed(sum(shape))
+    a = torch.rand(shape, generator=g).to(dev)
+    b = (a + 0.2 * torch.randn(shape, generator=g).to(dev)).clamp(0, 1) if shape[2] > 20 else torch.rand(shape, generator=g).to(dev)
+    C1, C2 = 0.01 ** 2, 0.03 ** 2
+    m0, d0, e0, f0 = ref.fusedssim(C1, C2, a, b, True)
+    m1, d1, e1, f1 = fusedssim(C1, C2, a, b, True)
+    # the value map is O(1); the derivative maps reach ~1/C2 and dm_dmu1 is a difference of terms far larger than the
+    # result (the reference sums four of them with approximate divisions), so they are compared relative to the
+    # largest magnitude in the tensor
+    for name, x, y, rel in (("ssim_map", m1, m0, 2e-6), ("dm_dmu1", d1, d0, 2e-5), ("dm_dsigma1_sq", e1, e0, 2e-5),
+                            ("dm_dsigma12", f1, f0, 2e-5)):
+        tol = rel * max(1.0, float(y.abs().max()))
+        assert float((x - y).abs().max()) <= tol, (name, float((x - y).abs().max()), tol)
+    dL = torch.randn(shape, generator=g).to(dev)
+    g0 = ref.fusedssim_backward(C1, C2, a, b, dL, d0, e0, f0)
+    g1 = fusedssim_backward(C1, C2, a, b, dL, d0, e0, f0)         # same derivative maps in: isolates the backward kernel
+    assert float((g1 - g0).abs().max()) <= 2e-6 * max(1.0, float(g0.abs().max()))
+    # the public entry point end to end; whose error a deviation is, is decided by a float64 torch evaluation
+    x0, x1 = a.clone().requires_grad_(True), a.clone().requires_grad_(True)
+    v0, v1 = ref.fused_ssim(x0, b), fused_ssim(x1, b)
+    v0.backward(); v1.backward()
+    assert abs(v0.item() - v1.item()) < 2e-6
+    if a.numel() <= 20_000_000:
+        xd = a.double().requires_grad_(True)
+        vd = torch_ssim_map(xd, b.double()).mean()
+        vd.backward()
+        e_ours, e_ref = float((x1.grad.double() - xd.grad).abs().max()), float((x0.grad.double() - xd.grad).abs().max())
+        assert abs(v1.item() - vd.item()) <= 2 * abs(v0.item() - vd.item()) + 1e-6
+        assert e_ours <= 2 * e_ref + 1e-9 * float(xd.grad.abs().max()) + 1e-12, (e_ours, e_ref)
+    else:
+        assert float((x0.grad - x1.grad).abs().max()) <= 2e-5 * float(x0.grad.abs().max()) + 1e-12
+    if shape[2] > 10 and shape[3] > 10:
+        assert abs(ref.fused_ssim(a, b, padding="valid", train=False).item() - fused_ssim(a, b, padding="valid", train=False).item()) < 2e-6
