@@ -405,7 +405,7 @@ def frame_record(name, impl_kind, dev, steps):
     d = make_inputs(scene, cam, dev)
     flush = L2Flusher(dev)
     step = {"ours": lambda: step_ours(d, cam), "stock": lambda: step_ref_stock(d, cam), "shim": lambda: step_ref(d, cam)}[impl_kind]
-    ms = timed_steps(step, steps, 3, flush, dev)
+    ms = timed_steps(step, steps, 5, flush, dev)
     med = float(np.median(ms))
     f, _ = step()
     torch.cuda.synchronize(dev)
@@ -492,8 +492,9 @@ def live_traffic(kernel_regex, timeout_s=240):
             vals = {}
             with open(log) as fh:
                 rows = [r for r in csv.reader(l for l in fh if not l.startswith("=="))]
-            hdr = rows[0]
-            for r in rows[1:]:
+            h0 = next(i for i, r in enumerate(rows) if "Metric Name" in r and "Metric Value" in r)
+            hdr = rows[h0]
+            for r in rows[h0 + 1:]:
                 row = dict(zip(hdr, r))
                 v = float(row["Metric Value"].replace(",", ""))
                 unit = row.get("Metric Unit", "")
@@ -686,7 +687,7 @@ def main():
             out["ssim"] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
         if kind == "ours":
             torch.cuda.synchronize(dev)
-            lt = live_traffic({"render_bwd": "render_bwd_kernel", "render_fwd": "render_fwd_kernel"}.get(dom, dom))
+            lt = live_traffic({"render_bwd": "render_bwd", "render_fwd": "render_fwd"}.get(dom, dom))
             if lt is not None:
                 out["roofline"].update(traffic=lt["traffic"], traffic_source="ncu subprocess in this run (one launch, "
                                        "dram__bytes_read.sum + dram__bytes_write.sum)")

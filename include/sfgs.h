@@ -41,7 +41,7 @@
 extern "C" {
 #endif
 
-#define SFGS_VERSION 2          /* 2: out_norm_raw / norm_raw, two-phase backward, activations, geometry-free scratch allocator */
+#define SFGS_VERSION 3          /* 3: appearance_forward, overflow_reruns, selftest_expf; 2: out_norm_raw / norm_raw, two-phase backward, activations */
 #define SFGS_TILE 16          /* BLOCK_X = BLOCK_Y = 16, RAST/cuda_rasterizer/config.h:15-17 */
 #define SFGS_MAX_EXTRA 34     /* MAX_EXTRA_DIMS, RAST/cuda_rasterizer/auxiliary.h:20 */
 
@@ -238,6 +238,20 @@ int sfgs_activations_backward(int P, const float* opacity_raw, const float* scal
                               const double* filter_3D, const float* g_opacity, const float* g_scales,
                               const float* g_rotations, float* g_opacity_raw, float* g_scaling_raw,
                               float* g_rotation_raw, void* stream);
+
+/* ---- appearance path ----------------------------------
+ * The --appearance_enabled branch of render() (gaussian_renderer/__init__.py:105-118), forward, as one tensor-core
+ * kernel: EmbeddingModel.forward (scene/gaussian_model.py:45-69: [P,59] -> 128 -> 128 -> 6 MLP on [min(dc,1) | Fourier
+ * features | per-camera embedding], x0.01, offset/C0 on the DC term, per-channel multiplier, clamp at 1), eval_sh of
+ * the toned coefficients along normalize(xyz - campos) (utils/sh_utils.py), +0.5, clamp at 0  ->  colors_precomp [P,3].
+ * W1 is [128, 3+G+E] row-major (torch.nn.Linear.weight), W2 [128,128], W3 [6,128]; features [P,M,3] with M = 16,
+ * gemb [P,G] with G = 24 (4 Fourier frequencies), aemb [E] with E = 32; D = active SH degree.  bf16 tensor-core
+ * operands, fp32 accumulation (tcgen05.mma, accumulator in TMEM); the result is within 5e-4 of the float32 torch
+ * evaluation.  features and gemb must be 16-byte aligned. */
+int sfgs_appearance_forward(int P, int D, int M, const float* features, const float* gemb, int G, const float* aemb,
+                            int E, const float* W1, const float* b1, const float* W2, const float* b2,
+                            const float* W3, const float* b3, const float* means3D, const float* campos,
+                            float* colors, void* stream);
 
 /* ---- fused SSIM ---------------------------------------------------------- */
 int sfgs_fusedssim_forward(float C1, float C2, int B, int CH, int H, int W,

@@ -144,55 +144,63 @@ __device__ __forceinline__ float4 cov2d_project(float mx, float my, float mz,
 // (read off oracle/_ref, preprocessCUDA<3>, section after the three IEEE divisions of the view direction), pinned
 // with round-to-nearest intrinsics so the compiler cannot contract it differently: colours, and therefore the clamp
 // flags, are bit-identical to the reference (tests: rgb compared bit for bit on every visible Gaussian).
-__device__ __forceinline__ void sh_to_rgb(int deg, const float* __restrict__ sh /* [M][3] */,
+template <typename ShGet>
+__device__ __forceinline__ void sh_to_rgb(int deg, ShGet sh /* sh(j) = coefficient j/3, channel j%3 */,
                                           float px, float py, float pz, float cx, float cy, float cz,
                                           float rgb[3], unsigned& clamp_mask) {
   const float dx = __fsub_rn(px, cx), dy = __fsub_rn(py, cy), dz = __fsub_rn(pz, cz);
   // glm::length: dot = (x*x + y*y) + z*z, contracted as fma(z, z, fma(x, x, y*y))
   const float len = __fsqrt_rn(__fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy))));
   const float x = __fdiv_rn(dx, len), y = __fdiv_rn(dy, len), z = __fdiv_rn(dz, len);
-  float c[16];   // basis value times its constant, in the reference's association order
-  c[0] = SH_C0;
+  float r0 = __fmul_rn(sh(0), SH_C0), r1 = __fmul_rn(sh(1), SH_C0), r2 = __fmul_rn(sh(2), SH_C0);
+  // one fused multiply-add per coefficient and channel, coefficients in ascending order (the three channels are
+  // independent chains); each basis value is formed in the reference's association order and used at once
+#define SH_ACC(k, c) { const float c_ = (c); r0 = __fmaf_rn(c_, sh(3 * (k)), r0); r1 = __fmaf_rn(c_, sh(3 * (k) + 1), r1); r2 = __fmaf_rn(c_, sh(3 * (k) + 2), r2); }
   if (deg > 0) {
-    c[1] = -__fmul_rn(y, SH_C1); c[2] = __fmul_rn(z, SH_C1); c[3] = -__fmul_rn(x, SH_C1);
+    SH_ACC(1, -__fmul_rn(y, SH_C1)); SH_ACC(2, __fmul_rn(z, SH_C1)); SH_ACC(3, -__fmul_rn(x, SH_C1));
     if (deg > 1) {
       const float xx = __fmul_rn(x, x), yy = __fmul_rn(y, y), zz = __fmul_rn(z, z);
       const float xy = __fmul_rn(x, y), yz = __fmul_rn(y, z), xz = __fmul_rn(x, z);
       const float zz2 = __fadd_rn(zz, zz);                                  // 2 zz (exact)
       const float xx_m_yy = __fsub_rn(xx, yy);
-      c[4] = __fmul_rn(xy, SH_C2_0);
-      c[5] = __fmul_rn(yz, SH_C2_1);
-      c[6] = __fmul_rn(__fsub_rn(__fsub_rn(zz2, xx), yy), SH_C2_2);         // (2zz - xx) - yy
-      c[7] = __fmul_rn(xz, SH_C2_3);
-      c[8] = __fmul_rn(xx_m_yy, SH_C2_4);
+      SH_ACC(4, __fmul_rn(xy, SH_C2_0));
+      SH_ACC(5, __fmul_rn(yz, SH_C2_1));
+      SH_ACC(6, __fmul_rn(__fsub_rn(__fsub_rn(zz2, xx), yy), SH_C2_2));     // (2zz - xx) - yy
+      SH_ACC(7, __fmul_rn(xz, SH_C2_3));
+      SH_ACC(8, __fmul_rn(xx_m_yy, SH_C2_4));
       if (deg > 2) {
-        const float zz4_m_xx_m_yy = __fsub_rn(__fmaf_rn(zz, 4.0f, -xx), yy);                    // fma(zz, 4, -xx) - yy
-        c[9] = __fmul_rn(__fmul_rn(y, SH_C3_0), __fmaf_rn(xx, 3.0f, -yy));                       // fma(xx, 3, -yy)
-        c[10] = __fmul_rn(__fmul_rn(xy, SH_C3_1), z);
-        c[11] = __fmul_rn(__fmul_rn(y, SH_C3_2), zz4_m_xx_m_yy);
-        c[12] = __fmul_rn(__fmul_rn(z, SH_C3_3), __fmaf_rn(yy, -3.0f, __fmaf_rn(xx, -3.0f, zz2)));   // (2zz - 3xx) - 3yy
-        c[13] = __fmul_rn(zz4_m_xx_m_yy, __fmul_rn(x, SH_C3_4));
-        c[14] = __fmul_rn(xx_m_yy, __fmul_rn(z, SH_C3_5));
-        c[15] = __fmul_rn(__fmul_rn(x, SH_C3_6), __fmaf_rn(yy, -3.0f, xx));                      // fma(yy, -3, xx)
+        const float zz4_m_xx_m_yy = __fsub_rn(__fmaf_rn(zz, 4.0f, -xx), yy);                       // fma(zz, 4, -xx) - yy
+        SH_ACC(9, __fmul_rn(__fmul_rn(y, SH_C3_0), __fmaf_rn(xx, 3.0f, -yy)));                      // fma(xx, 3, -yy)
+        SH_ACC(10, __fmul_rn(__fmul_rn(xy, SH_C3_1), z));
+        SH_ACC(11, __fmul_rn(__fmul_rn(y, SH_C3_2), zz4_m_xx_m_yy));
+        SH_ACC(12, __fmul_rn(__fmul_rn(z, SH_C3_3), __fmaf_rn(yy, -3.0f, __fmaf_rn(xx, -3.0f, zz2))));   // (2zz - 3xx) - 3yy
+        SH_ACC(13, __fmul_rn(zz4_m_xx_m_yy, __fmul_rn(x, SH_C3_4)));
+        SH_ACC(14, __fmul_rn(xx_m_yy, __fmul_rn(z, SH_C3_5)));
+        SH_ACC(15, __fmul_rn(__fmul_rn(x, SH_C3_6), __fmaf_rn(yy, -3.0f, xx)));                     // fma(yy, -3, xx)
       }
     }
   }
-  const int ncoef = (deg + 1) * (deg + 1);
-  clamp_mask = 0u;
-#pragma unroll
-  for (int ch = 0; ch < 3; ch++) {
-    float r = __fmul_rn(sh[ch], SH_C0);
-#pragma unroll
-    for (int k = 1; k < 16; k++)
-      if (k < ncoef) r = __fmaf_rn(c[k], sh[3 * k + ch], r);      // one fused multiply-add per coefficient, in order
-    // result += 0.5; clamped = result < 0; result = max(result, 0)   (forward.cu:63-70; the binary tests r < -0.5)
-    const float v = __fadd_rn(r, 0.5f);
-    if (v < 0.0f) clamp_mask |= 1u << ch;
-    rgb[ch] = (v < 0.0f) ? 0.0f : v;
-  }
+#undef SH_ACC
+  // result += 0.5; clamped = result < 0; result = max(result, 0)   (forward.cu:63-70; the binary tests r < -0.5)
+  const float v0 = __fadd_rn(r0, 0.5f), v1 = __fadd_rn(r1, 0.5f), v2 = __fadd_rn(r2, 0.5f);
+  clamp_mask = (v0 < 0.0f ? 1u : 0u) | (v1 < 0.0f ? 2u : 0u) | (v2 < 0.0f ? 4u : 0u);
+  rgb[0] = (v0 < 0.0f) ? 0.0f : v0; rgb[1] = (v1 < 0.0f) ? 0.0f : v1; rgb[2] = (v2 < 0.0f) ? 0.0f : v2;
 }
 
 constexpr int PRE_THREADS = 256;
+constexpr int PRE_SPAN = 1024;        // Gaussians per block: four per thread in the cull phase
+
+// Upper bound of the screen-space radius the exact projection can produce (for the conservative pre-cull).
+//   radius = ceil(3 sqrt(lambda_max)),  lambda_max <= mid + sqrt(max(0.1, mid^2 - det)) <= 2 mid + 0.32 = trace(cov2D') + 0.32,
+//   trace(cov2D') = trace(T Sigma T^T) + 2 k <= |J|_F^2 |W|_F^2 trace(Sigma) + 2 k   (T = W J, kernel_size k on the diagonal)
+//   |J|_F^2 = (fx^2 (1 + (tx/tz)^2) + fy^2 (1 + (ty/tz)^2)) / tz^2 with |tx/tz| <= 1.3 tan(fovx/2) after the reference's clamp.
+// Every factor is rounded up generously (1 %, +3 px): the bound only has to be safe, not tight — a Gaussian passes the
+// pre-cull when the tile rectangle of (centre, bound) is non-empty, and the exact path then decides.
+__device__ __forceinline__ float radius_bound(float trace_sigma, float view_z, float jw2 /* (fx^2(1+limx^2) + fy^2(1+limy^2)) |W|_F^2 */,
+                                              float kernel_size) {
+  const float tr2d = jw2 * trace_sigma / (view_z * view_z) * 1.01f + 2.f * kernel_size + 0.32f;
+  return 3.f * sqrtf(tr2d) + 3.f;
+}
 
 __global__ void __launch_bounds__(PRE_THREADS, 3)
 preprocess_kernel(int P, int D, int M,
@@ -203,188 +211,253 @@ preprocess_kernel(int P, int D, int M,
                   const float* __restrict__ viewmatrix, const float* __restrict__ projmatrix,
                   const float* __restrict__ cam_pos, int W, int H, float tan_fovx, float tan_fovy,
                   float focal_x, float focal_y, float kernel_size, int gx, int gy, int band0, int band1,
+                  int prefiltered,
                   int* __restrict__ radii, float* __restrict__ rec, float* __restrict__ cov3D_out,
                   unsigned char* __restrict__ clamped, uint32_t* __restrict__ tiles_touched,
                   uint32_t* __restrict__ tile_count, uint32_t* __restrict__ hdr, uint4* __restrict__ tmp,
                   unsigned long long capacity) {
-  const int idx_raw = blockIdx.x * PRE_THREADS + threadIdx.x;
-  const bool in_range = idx_raw < P;
-  const int idx = in_range ? idx_raw : P - 1;   // out-of-range lanes shadow the last Gaussian and write nothing
-  TileRect vis_rect = {0, 0, 0, 0};
-  float vis_depth = 0.f;
-
   extern __shared__ __align__(16) unsigned char pre_smem[];
   float4* s_sh = reinterpret_cast<float4*>(pre_smem);                                    // [12][PRE_THREADS]
   uint32_t* s_incl = reinterpret_cast<uint32_t*>(pre_smem + 12 * PRE_THREADS * sizeof(float4));
-  int4* s_rect = reinterpret_cast<int4*>(pre_smem + 12 * PRE_THREADS * sizeof(float4) + PRE_THREADS * sizeof(uint32_t));
-
-  // Every per-Gaussian input that does not depend on the cull is requested up front, so the kernel pays one
-  // DRAM latency instead of one per dependent branch (the kernel is latency-, not bandwidth-bound).
-  const float px = means3D[3 * idx], py = means3D[3 * idx + 1], pz = means3D[3 * idx + 2];
-  const bool need_sr = cov3D_precomp == nullptr || norm3D_precomp == nullptr;
-  float sx = 0.f, sy = 0.f, sz = 0.f;
-  float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (need_sr) {
-    sx = scales[3 * idx]; sy = scales[3 * idx + 1]; sz = scales[3 * idx + 2];
-    q = *reinterpret_cast<const float4*>(rotations + 4 * (size_t)idx);
-  }
-  const float opac_in = opacities[idx];
+  int4* s_rect = reinterpret_cast<int4*>(s_incl + PRE_THREADS);
+  uint32_t* s_gid = reinterpret_cast<uint32_t*>(s_rect + PRE_THREADS);
+  unsigned short* s_cand = reinterpret_cast<unsigned short*>(s_gid + PRE_THREADS);        // [PRE_SPAN]
+  __shared__ int s_wcnt[4][PRE_THREADS / 32];
   const float* vm = viewmatrix;
   const float* pm = projmatrix;
+  const int tid = threadIdx.x;
+  const unsigned lane = tid & 31u, wid = tid >> 5;
+  const int base = blockIdx.x * PRE_SPAN;
+
+  // ================= phase A: conservative cull, four Gaussians per thread (independent load chains) =================
+  // 64 % of the 1M benchmark frame and 93 % of the 5M frame never reach the image.  Running the exact projection
+  // thread-per-Gaussian makes every warp pay the full path for its few visible lanes; instead all Gaussians take this
+  // cheap test (centre, view depth, a safe radius bound) and only the candidates — compacted in index order — run the
+  // exact path in dense warps below.  A non-candidate provably has an empty tile rectangle: radius 0, no tiles.
+  const float limx = 1.3f * tan_fovx, limy = 1.3f * tan_fovy;
+  const float wf2 = vm[0] * vm[0] + vm[1] * vm[1] + vm[2] * vm[2] + vm[4] * vm[4] + vm[5] * vm[5] + vm[6] * vm[6] +
+                    vm[8] * vm[8] + vm[9] * vm[9] + vm[10] * vm[10];
+  const float jw2 = (focal_x * focal_x * (1.f + limx * limx) + focal_y * focal_y * (1.f + limy * limy)) * wf2;
+  unsigned cand_bits = 0;          // bit j: Gaussian base + j*256 + tid is a candidate
+#pragma unroll 1
+  for (int j = 0; j < 4; j++) {
+    const int i = base + j * PRE_THREADS + tid;
+    bool cand_j = false;
+    if (i < P) {
+      const float px = means3D[3 * (size_t)i], py = means3D[3 * (size_t)i + 1], pz = means3D[3 * (size_t)i + 2];
+      const float view_z = vm[2] * px + vm[6] * py + vm[10] * pz + vm[14];
+      if (prefiltered && !(view_z > 0.2f)) hdr[HDR_PREFILTER] = 1u;     // the reference traps (auxiliary.h:157-161)
+      if (view_z > 0.199f) {                                            // 0.2 with a margin: the exact test follows
+        const float hx = pm[0] * px + pm[4] * py + pm[8] * pz + pm[12];
+        const float hy = pm[1] * px + pm[5] * py + pm[9] * pz + pm[13];
+        const float hw = pm[3] * px + pm[7] * py + pm[11] * pz + pm[15];
+        const float p_w = 1.0f / (hw + 0.0000001f);
+        const float pix_x = ndc_to_pix(hx * p_w, W), pix_y = ndc_to_pix(hy * p_w, H);
+        float trace_sigma;
+        if (cov3D_precomp != nullptr) {
+          const float* c = cov3D_precomp + 6 * (size_t)i;
+          trace_sigma = c[0] + c[3] + c[5];
+        } else {
+          const float sx = scales[3 * (size_t)i], sy = scales[3 * (size_t)i + 1], sz = scales[3 * (size_t)i + 2];
+          const float4 q = *reinterpret_cast<const float4*>(rotations + 4 * (size_t)i);
+          float R[3][3];
+          rot_from_quat(q.x, q.y, q.z, q.w, R);
+          // trace(Sigma) = sum_r (mod s_r)^2 sum_c R[c][r]^2
+          const float n0 = R[0][0] * R[0][0] + R[1][0] * R[1][0] + R[2][0] * R[2][0];
+          const float n1 = R[0][1] * R[0][1] + R[1][1] * R[1][1] + R[2][1] * R[2][1];
+          const float n2 = R[0][2] * R[0][2] + R[1][2] * R[1][2] + R[2][2] * R[2][2];
+          trace_sigma = scale_modifier * scale_modifier * (sx * sx * n0 + sy * sy * n1 + sz * sz * n2);
+        }
+        const float rb = radius_bound(fabsf(trace_sigma), view_z, jw2, kernel_size);
+        if (!(rb < 1.0e9f) || !(fabsf(pix_x) < 1.0e9f) || !(fabsf(pix_y) < 1.0e9f)) cand_j = true;   // inf / NaN: let the exact path decide
+        else {
+          const TileRect r = tile_rect(pix_x, pix_y, (int)rb + 1, gx, gy);
+          cand_j = (r.x1 - r.x0) * (r.y1 - r.y0) != 0;
+        }
+      }
+      if (!cand_j) { radii[i] = 0; tiles_touched[i] = 0u; }
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, cand_j);
+    if (lane == 0) s_wcnt[j][wid] = __popc(bal);
+    // rank of this lane among the warp's candidates of pass j, parked in the upper bits
+    if (cand_j) cand_bits |= (1u << j) | ((unsigned)__popc(bal & ((1u << lane) - 1u)) << (4 + 5 * j));
+  }
+  __syncthreads();
+  int ncand = 0;
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    int off = ncand;
+#pragma unroll
+    for (int w = 0; w < PRE_THREADS / 32; w++) { off += (w < (int)wid) ? s_wcnt[j][w] : 0; ncand += s_wcnt[j][w]; }
+    if ((cand_bits >> j) & 1u) s_cand[off + ((cand_bits >> (4 + 5 * j)) & 31u)] = (unsigned short)(j * PRE_THREADS + tid);
+  }
+  __syncthreads();
+
+  // ================= phase B: exact projection of the candidates, dense warps =================
+  const bool need_sr = cov3D_precomp == nullptr || norm3D_precomp == nullptr;
   // 192 contiguous, 16-byte aligned bytes of SH per Gaussian: staged by cp.async into this thread's own
   // shared-memory column while the covariance math runs
   const bool sh_staged = colors_precomp == nullptr && M == 16 && (reinterpret_cast<uintptr_t>(shs) & 15) == 0;
   const int sh_nq = D == 0 ? 1 : (D == 1 ? 3 : (D == 2 ? 7 : 12));   // float4s covering (D+1)^2 coefficients
+  const unsigned wbase = tid & ~31u;
 
-  int out_radius = 0;
-  uint32_t out_tiles = 0;
+  for (int k0 = 0; k0 < ncand; k0 += PRE_THREADS) {     // block-uniform trip count
+    const int k = k0 + tid;
+    const bool in_range = k < ncand;
+    const int idx = base + (int)s_cand[in_range ? k : 0];
+    TileRect vis_rect = {0, 0, 0, 0};
+    float vis_depth = 0.f;
+    int out_radius = 0;
+    uint32_t out_tiles = 0;
 
-  const float view_z = vm[2] * px + vm[6] * py + vm[10] * pz + vm[14];
-  bool sh_in_flight = false;
-  auto stage_sh = [&]() {
-    const float4* s4 = reinterpret_cast<const float4*>(shs + (size_t)idx * 48);
+    if (in_range) {
+      if (sh_staged) {
+        const float4* s4 = reinterpret_cast<const float4*>(shs + (size_t)idx * 48);
 #pragma unroll
-    for (int k = 0; k < 12; k++)
-      if (k < sh_nq) {
-        const unsigned sa = (unsigned)__cvta_generic_to_shared(&s_sh[k * PRE_THREADS + threadIdx.x]);
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(s4 + k));
-      }
-    asm volatile("cp.async.commit_group;\n" ::);
-  };
-  if (in_range && view_z > 0.2f) {
-    const float hx = pm[0] * px + pm[4] * py + pm[8] * pz + pm[12];
-    const float hy = pm[1] * px + pm[5] * py + pm[9] * pz + pm[13];
-    const float hw = pm[3] * px + pm[7] * py + pm[11] * pz + pm[15];
-    const float p_w = 1.0f / (hw + 0.0000001f);
-    const float proj_x = hx * p_w, proj_y = hy * p_w;
-    // speculative: a centre within 1.25x of the image almost always ends up with a non-empty tile rectangle;
-    // anything the guess misses is staged later, anything it over-fetches is only wasted bandwidth
-    if (sh_staged && fabsf(proj_x) < 1.25f && fabsf(proj_y) < 1.25f) { stage_sh(); sh_in_flight = true; }
-
-    Sym3 V;
-    if (cov3D_precomp != nullptr) {
-      const float* c = cov3D_precomp + 6 * (size_t)idx;
-      V.c0 = c[0]; V.c1 = c[1]; V.c2 = c[2]; V.c3 = c[3]; V.c4 = c[4]; V.c5 = c[5];
-    } else {
-      V = cov3d_from_scale_rot(sx, sy, sz, scale_modifier, q.x, q.y, q.z, q.w);
-      float* co = cov3D_out + 6 * (size_t)idx;
-      co[0] = V.c0; co[1] = V.c1; co[2] = V.c2; co[3] = V.c3; co[4] = V.c4; co[5] = V.c5;
-    }
-
-    const float4 cov = cov2d_project(px, py, pz, focal_x, focal_y, tan_fovx, tan_fovy, kernel_size, V, vm);
-    const float det = (cov.x * cov.z - cov.y * cov.y);
-    if (det != 0.0f) {
-      const float det_inv = 1.f / det;
-      const float conx = cov.z * det_inv, cony = -cov.y * det_inv, conz = cov.x * det_inv;
-      const float mid = 0.5f * (cov.x + cov.z);
-      const float lambda1 = mid + sqrt(max(0.1f, mid * mid - det));
-      const float lambda2 = mid - sqrt(max(0.1f, mid * mid - det));
-      const float my_radius = ceil(3.f * sqrt(max(lambda1, lambda2)));
-      const float pix_x = ndc_to_pix(proj_x, W), pix_y = ndc_to_pix(proj_y, H);
-      const int iradius = my_radius;
-      const TileRect r = tile_rect(pix_x, pix_y, iradius, gx, gy);
-      const uint32_t ntiles_full = (uint32_t)((r.x1 - r.x0) * (r.y1 - r.y0));
-      // screen-space shard: this rank only bins the tile rows [band0, band1)
-      TileRect rb = r;
-      rb.y0 = max(r.y0, band0); rb.y1 = min(r.y1, band1);
-      const uint32_t ntiles = rb.y1 > rb.y0 ? (uint32_t)((rb.x1 - rb.x0) * (rb.y1 - rb.y0)) : 0u;
-      if (ntiles_full != 0) {
-        float n[3];
-        if (norm3D_precomp != nullptr) {
-          n[0] = norm3D_precomp[3 * idx]; n[1] = norm3D_precomp[3 * idx + 1]; n[2] = norm3D_precomp[3 * idx + 2];
-        } else {
-          normal_from_scale_rot(sx, sy, sz, q.x, q.y, q.z, q.w, px, py, pz, cam_pos[0], cam_pos[1], cam_pos[2], n);
-        }
-        float rgb[3];
-        unsigned cmask = 0;
-        if (colors_precomp == nullptr) {
-          const float* shp = shs + (size_t)idx * M * 3;
-          if (sh_staged) {
-            float shl[48];
-            if (!sh_in_flight) stage_sh();
-            asm volatile("cp.async.wait_group 0;\n" ::: "memory");
-#pragma unroll
-            for (int k = 0; k < 12; k++) {
-              float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (k < sh_nq) v = s_sh[k * PRE_THREADS + threadIdx.x];
-              shl[4 * k] = v.x; shl[4 * k + 1] = v.y; shl[4 * k + 2] = v.z; shl[4 * k + 3] = v.w;
-            }
-            sh_to_rgb(D, shl, px, py, pz, cam_pos[0], cam_pos[1], cam_pos[2], rgb, cmask);
-          } else {
-            sh_to_rgb(D, shp, px, py, pz, cam_pos[0], cam_pos[1], cam_pos[2], rgb, cmask);
+        for (int q4 = 0; q4 < 12; q4++)
+          if (q4 < sh_nq) {
+            const unsigned sa = (unsigned)__cvta_generic_to_shared(&s_sh[q4 * PRE_THREADS + tid]);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(s4 + q4));
           }
-        } else {
-          rgb[0] = colors_precomp[3 * idx]; rgb[1] = colors_precomp[3 * idx + 1]; rgb[2] = colors_precomp[3 * idx + 2];
-        }
-        clamped[idx] = (unsigned char)cmask;
+        asm volatile("cp.async.commit_group;\n" ::);
+      }
+      const float px = means3D[3 * (size_t)idx], py = means3D[3 * (size_t)idx + 1], pz = means3D[3 * (size_t)idx + 2];
+      float sx = 0.f, sy = 0.f, sz = 0.f;
+      float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (need_sr) {
+        sx = scales[3 * (size_t)idx]; sy = scales[3 * (size_t)idx + 1]; sz = scales[3 * (size_t)idx + 2];
+        q = *reinterpret_cast<const float4*>(rotations + 4 * (size_t)idx);
+      }
+      const float opac_in = opacities[idx];
+      const float view_z = vm[2] * px + vm[6] * py + vm[10] * pz + vm[14];
+      if (view_z > 0.2f) {
+        const float hx = pm[0] * px + pm[4] * py + pm[8] * pz + pm[12];
+        const float hy = pm[1] * px + pm[5] * py + pm[9] * pz + pm[13];
+        const float hw = pm[3] * px + pm[7] * py + pm[11] * pz + pm[15];
+        const float p_w = 1.0f / (hw + 0.0000001f);
+        const float proj_x = hx * p_w, proj_y = hy * p_w;
 
-        float4* o = reinterpret_cast<float4*>(rec + (size_t)idx * REC_FLOATS);
-        o[0] = make_float4(pix_x, pix_y, conx, cony);
-        o[1] = make_float4(conz, opac_in * cov.w, view_z, 0.f);
-        o[2] = make_float4(rgb[0], rgb[1], rgb[2], n[0]);
-        o[3] = make_float4(n[1], n[2], 0.f, 0.f);
-        out_radius = iradius;
-        out_tiles = ntiles;
-        vis_rect = rb;
-        vis_depth = view_z;
+        Sym3 V;
+        if (cov3D_precomp != nullptr) {
+          const float* c = cov3D_precomp + 6 * (size_t)idx;
+          V.c0 = c[0]; V.c1 = c[1]; V.c2 = c[2]; V.c3 = c[3]; V.c4 = c[4]; V.c5 = c[5];
+        } else {
+          V = cov3d_from_scale_rot(sx, sy, sz, scale_modifier, q.x, q.y, q.z, q.w);
+        }
+
+        const float4 cov = cov2d_project(px, py, pz, focal_x, focal_y, tan_fovx, tan_fovy, kernel_size, V, vm);
+        const float det = (cov.x * cov.z - cov.y * cov.y);
+        if (det != 0.0f) {
+          const float det_inv = 1.f / det;
+          const float conx = cov.z * det_inv, cony = -cov.y * det_inv, conz = cov.x * det_inv;
+          const float mid = 0.5f * (cov.x + cov.z);
+          const float lambda1 = mid + sqrt(max(0.1f, mid * mid - det));
+          const float lambda2 = mid - sqrt(max(0.1f, mid * mid - det));
+          const float my_radius = ceil(3.f * sqrt(max(lambda1, lambda2)));
+          const float pix_x = ndc_to_pix(proj_x, W), pix_y = ndc_to_pix(proj_y, H);
+          const int iradius = my_radius;
+          const TileRect r = tile_rect(pix_x, pix_y, iradius, gx, gy);
+          const uint32_t ntiles_full = (uint32_t)((r.x1 - r.x0) * (r.y1 - r.y0));
+          // screen-space shard: this rank only bins the tile rows [band0, band1)
+          TileRect rb = r;
+          rb.y0 = max(r.y0, band0); rb.y1 = min(r.y1, band1);
+          const uint32_t ntiles = rb.y1 > rb.y0 ? (uint32_t)((rb.x1 - rb.x0) * (rb.y1 - rb.y0)) : 0u;
+          if (ntiles_full != 0) {
+            if (cov3D_precomp == nullptr) {
+              float* co = cov3D_out + 6 * (size_t)idx;
+              co[0] = V.c0; co[1] = V.c1; co[2] = V.c2; co[3] = V.c3; co[4] = V.c4; co[5] = V.c5;
+            }
+            float n[3];
+            if (norm3D_precomp != nullptr) {
+              n[0] = norm3D_precomp[3 * (size_t)idx]; n[1] = norm3D_precomp[3 * (size_t)idx + 1]; n[2] = norm3D_precomp[3 * (size_t)idx + 2];
+            } else {
+              normal_from_scale_rot(sx, sy, sz, q.x, q.y, q.z, q.w, px, py, pz, cam_pos[0], cam_pos[1], cam_pos[2], n);
+            }
+            float rgb[3];
+            unsigned cmask = 0;
+            if (colors_precomp == nullptr) {
+              if (sh_staged) {
+                asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+                // coefficient j sits in word (j & 3) of float4 [j >> 2][tid] of this thread's shared-memory column
+                const float* col = reinterpret_cast<const float*>(s_sh) + 4 * tid;
+                sh_to_rgb(D, [&](int j) { return col[(j >> 2) * (4 * PRE_THREADS) + (j & 3)]; }, px, py, pz, cam_pos[0],
+                          cam_pos[1], cam_pos[2], rgb, cmask);
+              } else {
+                const float* shp = shs + (size_t)idx * M * 3;
+                sh_to_rgb(D, [&](int j) { return shp[j]; }, px, py, pz, cam_pos[0], cam_pos[1], cam_pos[2], rgb, cmask);
+              }
+            } else {
+              rgb[0] = colors_precomp[3 * (size_t)idx]; rgb[1] = colors_precomp[3 * (size_t)idx + 1]; rgb[2] = colors_precomp[3 * (size_t)idx + 2];
+            }
+            clamped[idx] = (unsigned char)cmask;
+
+            float4* o = reinterpret_cast<float4*>(rec + (size_t)idx * REC_FLOATS);
+            o[0] = make_float4(pix_x, pix_y, conx, cony);
+            o[1] = make_float4(conz, opac_in * cov.w, view_z, 0.f);
+            o[2] = make_float4(rgb[0], rgb[1], rgb[2], n[0]);
+            o[3] = make_float4(n[1], n[2], 0.f, 0.f);
+            out_radius = iradius;
+            out_tiles = ntiles;
+            vis_rect = rb;
+            vis_depth = view_z;
+          }
+        }
       }
+      radii[idx] = out_radius;
+      tiles_touched[idx] = out_tiles;
     }
-  }
-  if (!in_range) out_tiles = 0;
-  if (in_range) {
-    radii[idx] = out_radius;
-    tiles_touched[idx] = out_tiles;
-  }
-  // ---- append this warp's tile instances to the unsorted list -----------------------------------
-  // One warp-aggregated atomic reserves the slots.  The warp's instances are then dealt out to the
-  // lanes round-robin (instance j -> owner found by a binary search over the inclusive prefix kept in
-  // shared memory), so a large splat no longer serialises its lane and 32 independent histogram
-  // atomics are in flight per step.  The histogram atomic (it replaces the per-Gaussian prefix sum of
-  // the reference) hands back the instance's slot inside its tile bucket: the later scatter needs none.
-  asm volatile("cp.async.wait_group 0;\n" ::: "memory");   // culled threads may still have copies in flight
-  const unsigned lane = threadIdx.x & 31u;
-  const unsigned wbase = threadIdx.x & ~31u;
-  uint32_t incl = out_tiles;
+    // ---- append this warp's tile instances to the unsorted list -----------------------------------
+    // One warp-aggregated atomic reserves the slots.  The warp's instances are then dealt out to the
+    // lanes round-robin (instance j -> owner found by a binary search over the inclusive prefix kept in
+    // shared memory), so a large splat no longer serialises its lane and 32 independent histogram
+    // atomics are in flight per step.  The histogram atomic (it replaces the per-Gaussian prefix sum of
+    // the reference) hands back the instance's slot inside its tile bucket: the later scatter needs none.
+    asm volatile("cp.async.wait_group 0;\n" ::: "memory");   // culled threads may still have copies in flight
+    uint32_t incl = out_tiles;
 #pragma unroll
-  for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= (unsigned)o) incl += y; }
-  const uint32_t warp_total = __shfl_sync(0xffffffffu, incl, 31);
-  if (warp_total == 0) return;
-  uint32_t warp_base = 0;
-  if (lane == 31) warp_base = atomicAdd(&hdr[HDR_TMP_COUNT], warp_total);
-  warp_base = __shfl_sync(0xffffffffu, warp_base, 31);
-  s_incl[threadIdx.x] = incl;
-  s_rect[threadIdx.x] = make_int4(vis_rect.x0, vis_rect.y0, vis_rect.x1 - vis_rect.x0, (int)__float_as_uint(vis_depth));
-  __syncwarp();
-  // four instances per lane and step, so four histogram atomics are in flight before the first result is needed
-  constexpr int APP = 4;
-  for (uint32_t j0 = lane; j0 < warp_total; j0 += 32 * APP) {
-    uint32_t t[APP], gid[APP], dep[APP], pos[APP];
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= (unsigned)o) incl += y; }
+    const uint32_t warp_total = __shfl_sync(0xffffffffu, incl, 31);
+    if (warp_total != 0) {
+      uint32_t warp_base = 0;
+      if (lane == 31) warp_base = atomicAdd(&hdr[HDR_TMP_COUNT], warp_total);
+      warp_base = __shfl_sync(0xffffffffu, warp_base, 31);
+      s_incl[tid] = incl;
+      s_rect[tid] = make_int4(vis_rect.x0, vis_rect.y0, vis_rect.x1 - vis_rect.x0, (int)__float_as_uint(vis_depth));
+      s_gid[tid] = (uint32_t)idx;
+      __syncwarp();
+      // four instances per lane and step, so four histogram atomics are in flight before the first result is needed
+      constexpr int APP = 4;
+      for (uint32_t j0 = lane; j0 < warp_total; j0 += 32 * APP) {
+        uint32_t t[APP], gid[APP], dep[APP], pos[APP];
 #pragma unroll
-    for (int u = 0; u < APP; u++) {
-      const uint32_t j = j0 + 32u * u;
-      t[u] = 0xffffffffu;
-      if (j < warp_total) {
-        // owner = first lane whose inclusive prefix exceeds j
-        int lo = 0;
+        for (int u = 0; u < APP; u++) {
+          const uint32_t j = j0 + 32u * u;
+          t[u] = 0xffffffffu;
+          if (j < warp_total) {
+            // owner = first lane whose inclusive prefix exceeds j
+            int lo = 0;
 #pragma unroll
-        for (int step = 16; step > 0; step >>= 1)
-          if (s_incl[wbase + lo + step - 1] <= j) lo += step;
-        const uint32_t excl = lo > 0 ? s_incl[wbase + lo - 1] : 0u;
-        const int4 rc = s_rect[wbase + lo];
-        const uint32_t k = j - excl;                       // k-th tile of the owner's rectangle, row-major
-        const uint32_t ty = k / (uint32_t)rc.z, tx = k - ty * (uint32_t)rc.z;
-        t[u] = (uint32_t)(rc.y + (int)ty) * (uint32_t)gx + (uint32_t)(rc.x + (int)tx);
-        gid[u] = (uint32_t)(blockIdx.x * PRE_THREADS) + wbase + (uint32_t)lo;
-        dep[u] = (uint32_t)rc.w;
+            for (int step = 16; step > 0; step >>= 1)
+              if (s_incl[wbase + lo + step - 1] <= j) lo += step;
+            const uint32_t excl = lo > 0 ? s_incl[wbase + lo - 1] : 0u;
+            const int4 rc = s_rect[wbase + lo];
+            const uint32_t kk = j - excl;                      // kk-th tile of the owner's rectangle, row-major
+            const uint32_t ty = kk / (uint32_t)rc.z, tx = kk - ty * (uint32_t)rc.z;
+            t[u] = (uint32_t)(rc.y + (int)ty) * (uint32_t)gx + (uint32_t)(rc.x + (int)tx);
+            gid[u] = s_gid[wbase + lo];
+            dep[u] = (uint32_t)rc.w;
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < APP; u++)
+          if (t[u] != 0xffffffffu) pos[u] = atomicAdd(&tile_count[t[u]], 1u);
+#pragma unroll
+        for (int u = 0; u < APP; u++) {
+          const unsigned long long slot = (unsigned long long)warp_base + j0 + 32u * u;
+          if (t[u] != 0xffffffffu && slot < capacity) tmp[slot] = make_uint4(gid[u], dep[u], t[u], pos[u]);
+        }
       }
-    }
-#pragma unroll
-    for (int u = 0; u < APP; u++)
-      if (t[u] != 0xffffffffu) pos[u] = atomicAdd(&tile_count[t[u]], 1u);
-#pragma unroll
-    for (int u = 0; u < APP; u++) {
-      const unsigned long long slot = (unsigned long long)warp_base + j0 + 32u * u;
-      if (t[u] != 0xffffffffu && slot < capacity) tmp[slot] = make_uint4(gid[u], dep[u], t[u], pos[u]);
+      __syncwarp();     // the warp's shared rows are rewritten by its next pass
     }
   }
 }
@@ -403,19 +476,23 @@ __global__ void mark_visible_kernel(int P, const float* __restrict__ means3D,
 void sfgs_launch_preprocess(const sfgs_forward_args* a, const GeomLayout& g, const ImageLayout& im,
                             const BinningLayout& b, unsigned long long capacity, float focal_x, float focal_y,
                             cudaStream_t st) {
-  const int blocks = (a->P + PRE_THREADS - 1) / PRE_THREADS;
-  constexpr size_t smem = PRE_THREADS * (12 * sizeof(float4) + sizeof(uint32_t) + sizeof(int4));
+  const int blocks = (a->P + PRE_SPAN - 1) / PRE_SPAN;
+  constexpr size_t smem = PRE_THREADS * (12 * sizeof(float4) + sizeof(uint32_t) + sizeof(int4) + sizeof(uint32_t)) +
+                          PRE_SPAN * sizeof(unsigned short);
   static SfgsPerDeviceOnce attr_once;   // function attributes are per device
   if (attr_once.first_use()) {
     cudaFuncSetAttribute(preprocess_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   }
+  // tile-row band of this call: (0, 0) = the whole image; begin == end != 0 = an empty band (nothing is binned)
+  const bool whole = a->tile_row_begin == 0 && a->tile_row_end == 0;
+  const int band0 = whole ? 0 : (a->tile_row_begin < im.tiles_y ? a->tile_row_begin : im.tiles_y);
+  const int band1 = whole ? im.tiles_y : (a->tile_row_end < im.tiles_y ? a->tile_row_end : im.tiles_y);
   SFGS_COUNT_LAUNCH();
   preprocess_kernel<<<blocks, PRE_THREADS, smem, st>>>(
       a->P, a->D, a->M, a->means3D, a->scales, a->scale_modifier, a->rotations, a->opacities, a->shs,
       a->cov3D_precomp, a->norm3D_precomp, a->colors_precomp, a->viewmatrix, a->projmatrix, a->cam_pos,
       a->width, a->height, a->tan_fovx, a->tan_fovy, focal_x, focal_y, a->kernel_size, im.tiles_x, im.tiles_y,
-      a->tile_row_end > a->tile_row_begin ? a->tile_row_begin : 0,
-      a->tile_row_end > a->tile_row_begin ? a->tile_row_end : im.tiles_y,
+      band0, band1, a->prefiltered,
       a->radii, g.rec, g.cov3D, g.clamped, g.tiles_touched, im.tile_count, im.hdr, b.tmp, capacity);
 }
 

@@ -256,6 +256,153 @@ render_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
   }
 }
 
+
+// =====================================================================================================================
+// Warp-private variant (the default path; the kernel above remains for extra_attrs and the TMA-staging experiment).
+// Same idea as render_bwd_warp_kernel (sfgs_render_bwd.cu): every warp walks the tile's sorted list itself, front to
+// back, keeps the positions whose reach mask has its block's bit, gathers them 16 at a time into a private
+// double-buffered slot (two lanes per 64-byte record, cp.async, overlapping the previous chunk's math) and blends the
+// chunk in slot order.  Nothing is block-wide: no __syncthreads, no per-record bit scanning, record parameters at
+// immediate offsets, and a warp whose 32 pixels are saturated stops scanning on its own.
+constexpr int F4_CH = 16;
+struct alignas(16) FwdWarpSmem {
+  float4 rec[2][F4_CH][4];      // 2 KB   the chunk's blend records, double buffered
+  uint32_t pos[2][F4_CH];       // 1-based list position of each slot
+  uint32_t list[64];            // ring of collected list positions
+};
+
+__global__ void __launch_bounds__(FWD_THREADS)
+render_fwd_warp_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list,
+                       const unsigned char* __restrict__ inst_mask, const uint32_t* __restrict__ hdr, int W, int H,
+                       int band0, const float* __restrict__ rec, const float* __restrict__ bg_color,
+                       float* __restrict__ out_color, float* __restrict__ out_depth, float* __restrict__ out_norm,
+                       float* __restrict__ out_norm_raw, float* __restrict__ out_alpha, uint32_t* __restrict__ n_contrib,
+                       const OutPeers peers) {
+  if (hdr[HDR_OVERFLOW]) return;
+  __shared__ FwdWarpSmem s_warp[FWD_THREADS / 32];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  FwdWarpSmem& S = s_warp[wid];
+  const int tiles_x = (W + SFGS_TILE - 1) / SFGS_TILE;
+  const int tile_y = blockIdx.y + band0;
+  const int tile = tile_y * tiles_x + blockIdx.x;
+  const int px = blockIdx.x * SFGS_TILE + (wid & 1) * 8 + (lane & 7);
+  const int py = tile_y * SFGS_TILE + (wid >> 1) * 4 + (lane >> 3);
+  const bool inside = px < W && py < H;
+  const uint32_t pix_id = (uint32_t)W * py + px;
+  const float pixfx = (float)px, pixfy = (float)py;
+
+  const uint2 range = ranges[tile];
+  const int total = (int)(range.y - range.x);
+
+  // see render_fwd_kernel: a finished pixel parks its transmittance in T_done and continues with T = 0
+  float T = inside ? 1.0f : 0.0f;
+  float T_done = 0.0f;
+  uint32_t last_contributor = 0;
+  float C0 = 0.f, C1 = 0.f, C2 = 0.f, Dp = 0.f, N0 = 0.f, N1 = 0.f, N2 = 0.f;
+  const SfgsExpConsts ek = sfgs_exp_consts(hdr[HDR_ZERO]);
+  const unsigned lt_mask = (1u << lane) - 1u;
+
+  int p = 0;                       // positions [p, total) are still unscanned
+  int head = 0, have = 0;          // ring of collected positions: [head, head + have)
+  auto scan_gather = [&](int buf) -> int {
+    while (have < F4_CH && p < total) {
+      const int pos = p + lane;
+      unsigned m = 0;
+      if (pos < total) m = inst_mask[range.x + pos];
+      const bool bit = (m >> wid) & 1u;
+      const unsigned b = __ballot_sync(0xffffffffu, bit);
+      if (bit) S.list[(head + have + __popc(b & lt_mask)) & 63] = (uint32_t)pos;
+      have += __popc(b);
+      p += 32;
+    }
+    __syncwarp();
+    const int n = min(have, F4_CH);
+    if (lane < 2 * n) {              // two lanes per 64-byte record
+      const int r = lane >> 1, hf = lane & 1;
+      const uint32_t pos = S.list[(head + r) & 63];
+      const uint32_t id = point_list[range.x + pos];
+      const float* src = rec + (size_t)id * REC_FLOATS + hf * 8;
+      cp_async16(&S.rec[buf][r][hf * 2], src);
+      cp_async16(&S.rec[buf][r][hf * 2 + 1], src + 4);
+      if (hf == 0) S.pos[buf][r] = pos + 1u;       // 1-based: the value n_contrib records
+    }
+    cp_async_commit();
+    head = (head + n) & 63;
+    have -= n;
+    return n;
+  };
+
+  int buf = 0;
+  int n_cur = scan_gather(0);
+  while (n_cur > 0) {
+    cp_async_wait<0>();
+    __syncwarp();                                   // chunk `buf` has landed and is visible to the whole warp
+    if (__all_sync(0xffffffffu, T == 0.0f)) break;  // every pixel of the block is saturated (or outside the image)
+    const int n_next = scan_gather(buf ^ 1);        // the next chunk's gather overlaps the math below
+#pragma unroll
+    for (int k = 0; k < F4_CH; k++) {
+      if (k < n_cur) {                              // warp-uniform
+        const float4 a = S.rec[buf][k][0];          // mx, my, con.x, con.y
+        const float4 c = S.rec[buf][k][1];          // con.z, opac, depth, -
+        const float dx = a.x - pixfx, dy = a.y - pixfy;
+        const float power = -0.5f * (a.z * dx * dx + c.x * dy * dy) - a.w * dx * dy;
+        if (!(power > 0.0f)) {
+          const float alpha = min(0.99f, c.y * sfgs_expf(power, ek));
+          if (!(alpha < 1.0f / 255.0f)) {
+            const float test_T = T * (1 - alpha);
+            if (test_T < 0.0001f) { T_done = fmaxf(T_done, T); T = 0.0f; }
+            else {
+              const float4 f = S.rec[buf][k][2];    // r, g, b, nx
+              const float4 g = S.rec[buf][k][3];    // ny, nz
+              const float w = alpha * T;            // see render_fwd_kernel for the association of each output
+              C0 = fmaf(f.x, w, C0); C1 = fmaf(f.y, w, C1); C2 = fmaf(f.z, w, C2);
+              Dp += c.z * alpha * T;
+              N0 = fmaf(f.w, w, N0); N1 = fmaf(g.x, w, N1); N2 = fmaf(g.y, w, N2);
+              T = test_T;
+              last_contributor = S.pos[buf][k];
+            }
+          }
+        }
+      }
+    }
+    buf ^= 1;
+    n_cur = n_next;
+  }
+  cp_async_wait<0>();                // nothing may still be landing in this CTA's shared memory when it exits
+  if (T == 0.0f) T = T_done;
+
+  if (inside) {
+    const size_t HW = (size_t)H * W;
+    n_contrib[pix_id] = last_contributor;
+    const float c0 = C0 + T * bg_color[0], c1 = C1 + T * bg_color[1], c2 = C2 + T * bg_color[2];
+    if (out_norm_raw != nullptr) {
+      out_norm_raw[0 * HW + pix_id] = N0;
+      out_norm_raw[1 * HW + pix_id] = N1;
+      out_norm_raw[2 * HW + pix_id] = N2;
+      const float d = fmaxf(sqrtf(N0 * N0 + N1 * N1 + N2 * N2), 1e-12f);
+      N0 = N0 / d; N1 = N1 / d; N2 = N2 / d;
+    }
+    if (peers.n > 0) {
+      for (int r = 0; r < peers.n; r++) {
+        float* f = peers.p[r];
+        f[0 * HW + pix_id] = c0; f[1 * HW + pix_id] = c1; f[2 * HW + pix_id] = c2;
+        f[3 * HW + pix_id] = Dp;
+        f[4 * HW + pix_id] = 1 - T;
+        f[5 * HW + pix_id] = N0; f[6 * HW + pix_id] = N1; f[7 * HW + pix_id] = N2;
+      }
+    } else {
+      out_alpha[pix_id] = 1 - T;
+      out_color[0 * HW + pix_id] = c0;
+      out_color[1 * HW + pix_id] = c1;
+      out_color[2 * HW + pix_id] = c2;
+      out_depth[pix_id] = Dp;
+      out_norm[0 * HW + pix_id] = N0;
+      out_norm[1 * HW + pix_id] = N1;
+      out_norm[2 * HW + pix_id] = N2;
+    }
+  }
+}
+
 }  // namespace
 
 void sfgs_launch_render_fwd(const sfgs_forward_args* a, const GeomLayout& g, const ImageLayout& im,
@@ -268,6 +415,14 @@ void sfgs_launch_render_fwd(const sfgs_forward_args* a, const GeomLayout& g, con
   if (a->out_peers != nullptr && a->n_out_peers > 0)
     for (op.n = 0; op.n < a->n_out_peers && op.n < 8; op.n++) op.p[op.n] = a->out_peers[op.n];
   SFGS_COUNT_LAUNCH();
+#if !SFGS_TMA_STAGING
+  if (a->ED == 0) {   // default path: warp-private pipelines (render_fwd_warp_kernel)
+    render_fwd_warp_kernel<<<grid, FWD_THREADS, 0, st>>>(im.ranges, b.point_list, b.inst_mask, im.hdr, a->width, a->height, band0,
+                                                        g.rec, a->background, a->out_color, a->out_depth, a->out_norm,
+                                                        a->out_norm_raw, a->out_alpha, im.n_contrib, op);
+    return;
+  }
+#endif
   if (a->ED > 0)
     render_fwd_kernel<true><<<grid, FWD_THREADS, 0, st>>>(im.ranges, b.point_list, b.inst_mask, im.hdr, a->width, a->height, a->ED, band0,
                                                          g.rec, a->extra_attrs, a->background, a->out_color,

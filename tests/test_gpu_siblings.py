@@ -114,8 +114,9 @@ def test_fused_ssim_against_the_reference_cuda_kernel(cuda_device, shape):
     """The reference's own compiled fused-ssim (SSIM/ssim.cu, built by oracle/build_ref_torch.py with its setup.py's
     flags) as the oracle, first on its own test workload (SSIM/tests/test.py:81-83: B=5, CH=5, 1080x1920), then on
     the training shape and on sizes that are off the tile grid, odd, narrower than a tile or not 16-byte rows (the
-    non-TMA load path).  The reference kernel is compiled with --use_fast_math (approximate divisions), so the
-    bar is its own accuracy: the map within 2e-6, the gradient within 1e-6 of its largest element."""
+    non-TMA load path).  The reference kernel is compiled with --use_fast_math (approximate divisions): the map agrees
+    within 1e-5 (the image tolerance of the north star), and for the end-to-end value and gradient a float64 torch
+    evaluation decides whose error a deviation is (ours <= 2x the reference kernel's)."""
     ref = _ref_fused_ssim()
     from fused_ssim import fused_ssim, fusedssim, fusedssim_backward
     dev = cuda_device
@@ -128,7 +129,7 @@ def test_fused_ssim_against_the_reference_cuda_kernel(cuda_device, shape):
     # the value map is O(1); the derivative maps reach ~1/C2 and dm_dmu1 is a difference of terms far larger than the
     # result (the reference sums four of them with approximate divisions), so they are compared relative to the
     # largest magnitude in the tensor
-    for name, x, y, rel in (("ssim_map", m1, m0, 2e-6), ("dm_dmu1", d1, d0, 2e-5), ("dm_dsigma1_sq", e1, e0, 2e-5),
+    for name, x, y, rel in (("ssim_map", m1, m0, 1e-5), ("dm_dmu1", d1, d0, 2e-5), ("dm_dsigma1_sq", e1, e0, 2e-5),
                             ("dm_dsigma12", f1, f0, 2e-5)):
         tol = rel * max(1.0, float(y.abs().max()))
         assert float((x - y).abs().max()) <= tol, (name, float((x - y).abs().max()), tol)

@@ -6,7 +6,7 @@ mkdir -p gpurun_out
 for step in "$@"; do
   case $step in
     newtests)  timeout 1500 python -m pytest tests/test_gpu_parity.py -m gpu -q -s -k "benched or needles or adjudicated or randomised or golden" > gpurun_out/${tag}_newtests.log 2>&1; echo "newtests rc=$?" ;;
-    alltests)  timeout 1800 python -m pytest tests -m gpu -q -x > gpurun_out/${tag}_alltests.log 2>&1; echo "alltests rc=$?"; tail -5 gpurun_out/${tag}_alltests.log ;;
+    alltests)  timeout 1800 python -m pytest tests -m gpu -q > gpurun_out/${tag}_alltests.log 2>&1; echo "alltests rc=$?"; tail -5 gpurun_out/${tag}_alltests.log ;;
     bench)     timeout 600 python bench.py > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err; echo "bench rc=$?"; cat gpurun_out/${tag}_bench.json | head -c 3000 ;;
     benchref)  timeout 600 python bench.py --impl reference > gpurun_out/${tag}_benchref.json 2> gpurun_out/${tag}_benchref.err; echo "benchref rc=$?"; cat gpurun_out/${tag}_benchref.json | head -c 1500 ;;
     host)      timeout 300 python tools/host_overhead.py > gpurun_out/${tag}_host.log 2>&1; echo "host rc=$?"; head -40 gpurun_out/${tag}_host.log ;;
