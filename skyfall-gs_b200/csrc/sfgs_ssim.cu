@@ -86,45 +86,75 @@ struct Maps4 { CUtensorMap m[4]; };
 
 // ---------------------------------------------------------------------------------------------------- forward
 struct FwdSmem {
-  float box[2][BOX_STRIDE];          // img1, img2 tile + halo (TMA destination, dense rows of BOX_W floats)
+  float box[2][2][BOX_STRIDE];       // [stage][img1, img2] tile + halo (TMA destination, dense rows of BOX_W floats)
   float2 h12[BOX_H][TW];             // horizontally filtered (x, y)
   float2 h34[BOX_H][TW];             // horizontally filtered (x^2, y^2)
   float h5[BOX_H][TW];               // horizontally filtered x*y
-  u64 bar;
+  u64 bar[2];
+};
+
+// Persistent CTAs: CTA b takes tiles b, b + grid, ...; the boxes of tile i+1 are requested from the TMA unit before
+// tile i is touched (two box stages, one mbarrier each), so the fetch latency hides behind a whole tile of arithmetic.
+struct TileIter {
+  int tiles_x, tiles_y, ntiles;
+  __device__ __forceinline__ void decode(int tile, int& x0, int& y0, int& plane) const {
+    const int per_plane = tiles_x * tiles_y;
+    plane = tile / per_plane;
+    const int r = tile - plane * per_plane;
+    const int ty = r / tiles_x;
+    x0 = (r - ty * tiles_x) * TW; y0 = ty * TH;
+  }
 };
 
 template <bool TRAIN, bool USE_TMA>
 __global__ void __launch_bounds__(SSIM_THREADS, 2)
-ssim_fwd_kernel(const __grid_constant__ Maps4 tm, int H, int W, float C1, float C2, const float* __restrict__ img1,
+ssim_fwd_kernel(const __grid_constant__ Maps4 tm, int H, int W, int planes, float C1, float C2, const float* __restrict__ img1,
                 const float* __restrict__ img2, float* __restrict__ ssim_map, float* __restrict__ dm_dmu1,
                 float* __restrict__ dm_dsigma1_sq, float* __restrict__ dm_dsigma12) {
   extern __shared__ __align__(128) unsigned char ssim_smem[];
   FwdSmem& S = *reinterpret_cast<FwdSmem*>(ssim_smem);
   const int t = threadIdx.x;
-  const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH, plane = blockIdx.z;
-  const size_t poff = (size_t)plane * H * W;
+  TileIter it;
+  it.tiles_x = (W + TW - 1) / TW; it.tiles_y = (H + TH - 1) / TH; it.ntiles = it.tiles_x * it.tiles_y * planes;
 
+  auto request = [&](int tile, int stage) {      // thread 0 only
+    int bx, by, pl;
+    it.decode(tile, bx, by, pl);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // earlier generic-proxy reads of this stage are ordered before the async writes
+    mbar_expect_tx(&S.bar[stage], 2u * BOX_FLOATS * sizeof(float));
+    tma_load_box(S.box[stage][0], &tm.m[0], bx - HX, by - HALO, pl, &S.bar[stage]);
+    tma_load_box(S.box[stage][1], &tm.m[1], bx - HX, by - HALO, pl, &S.bar[stage]);
+  };
   if (USE_TMA) {
     if (t == 0) {
-      mbar_init(&S.bar, 1);
+      mbar_init(&S.bar[0], 1); mbar_init(&S.bar[1], 1);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-      mbar_expect_tx(&S.bar, 2u * BOX_FLOATS * sizeof(float));
-      tma_load_box(S.box[0], &tm.m[0], x0 - HX, y0 - HALO, plane, &S.bar);
-      tma_load_box(S.box[1], &tm.m[1], x0 - HX, y0 - HALO, plane, &S.bar);
+      if ((int)blockIdx.x < it.ntiles) request(blockIdx.x, 0);
     }
-    __syncthreads();            // the barrier word is initialised before anyone polls it
-    mbar_wait(&S.bar, 0);
+    __syncthreads();            // the barrier words are initialised before anyone polls them
+  }
+
+  int iter = 0;
+  for (int tile = blockIdx.x; tile < it.ntiles; tile += gridDim.x, iter++) {
+  const int stage = iter & 1;
+  int x0, y0, plane;
+  it.decode(tile, x0, y0, plane);
+  const size_t poff = (size_t)plane * H * W;
+  if (USE_TMA) {
+    // the other stage was last read by the previous tile's horizontal pass, which every thread left two barriers ago
+    if (t == 0 && tile + (int)gridDim.x < it.ntiles) request(tile + gridDim.x, stage ^ 1);
+    mbar_wait(&S.bar[stage], (unsigned)(iter >> 1) & 1u);
   } else {
-    load_box_generic(S.box[0], img1 + poff, x0 - HX, y0 - HALO, W, H);
-    load_box_generic(S.box[1], img2 + poff, x0 - HX, y0 - HALO, W, H);
+    load_box_generic(S.box[stage][0], img1 + poff, x0 - HX, y0 - HALO, W, H);
+    load_box_generic(S.box[stage][1], img2 + poff, x0 - HX, y0 - HALO, W, H);
     __syncthreads();
   }
 
   // ---- horizontal pass: unit = (box row, group of 4 output columns); 14 inputs per image from five 128-bit loads
   for (int u = t; u < BOX_H * (TW / 4); u += SSIM_THREADS) {
     const int row = u >> 4, xg = u & 15;
-    const float4* px = reinterpret_cast<const float4*>(&S.box[0][row * BOX_W + 4 * xg]);
-    const float4* py = reinterpret_cast<const float4*>(&S.box[1][row * BOX_W + 4 * xg]);
+    const float4* px = reinterpret_cast<const float4*>(&S.box[stage][0][row * BOX_W + 4 * xg]);
+    const float4* py = reinterpret_cast<const float4*>(&S.box[stage][1][row * BOX_W + 4 * xg]);
     float X[20], Y[20];                       // box columns 4xg .. 4xg+19; the four outputs use columns 4xg+3 .. 4xg+16
 #pragma unroll
     for (int q = 0; q < 5; q++) {
@@ -214,7 +244,9 @@ ssim_fwd_kernel(const __grid_constant__ Maps4 tm, int H, int W, float C1, float 
       const float sigma1_sq = ex2 - mu1_sq, sigma2_sq = ey2 - mu2_sq, sigma12 = exy - mu12;
       const float A = mu1_sq + mu2_sq + C1, B = sigma1_sq + sigma2_sq + C2;
       const float Cn = 2.f * mu12 + C1, Dn = 2.f * sigma12 + C2;
-      const float iA = __frcp_rn(A), iB = __frcp_rn(B);
+      float iA, iB;       // A, B >= C1, C2 > 0: the approximate reciprocal (1 ulp) needs no special cases
+      asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(iA) : "f"(A));
+      asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(iB) : "f"(B));
       const float iAB = iA * iB;
       val[c] = Cn * Dn * iAB;
       if (TRAIN) {
@@ -241,45 +273,64 @@ ssim_fwd_kernel(const __grid_constant__ Maps4 tm, int H, int W, float C1, float 
         }
     }
   }
+  __syncthreads();      // the vertical pass is done with h12/h34/h5 before the next tile's horizontal pass rewrites them
+  }   // tile loop
 }
 
 // ---------------------------------------------------------------------------------------------------- backward
 // dL/dimg1 = G * (dmu1 dL) + 2 img1 . G * (dsigma1_sq dL) + img2 . G * (dsigma12 dL),  G = the 2-D window
 // (mu1 = G*x, sigma1_sq = G*x^2 - mu1^2, sigma12 = G*xy - mu1 mu2; the mu1 terms are inside dm_dmu1).
 struct BwdSmem {
-  float box[4][BOX_STRIDE];          // dL_dmap, dm_dmu1, dm_dsigma1_sq, dm_dsigma12 tiles + halo
+  float box[1][4][BOX_STRIDE];       // [dL_dmap, dm_dmu1, dm_dsigma1_sq, dm_dsigma12] tiles + halo (one stage: see below)
   float2 h01[BOX_H][TW];             // horizontally filtered (dmu1 dL, dsigma1_sq dL)
   float h2[BOX_H][TW];               // horizontally filtered dsigma12 dL
-  u64 bar;
+  u64 bar[2];
 };
 
+// Four input planes leave no room for two box stages at two CTAs per SM, so the boxes are single-buffered and the next
+// tile's fetch is issued as soon as the horizontal pass has consumed them: it overlaps the vertical pass and the stores.
 template <bool USE_TMA>
 __global__ void __launch_bounds__(SSIM_THREADS, 2)
-ssim_bwd_kernel(const __grid_constant__ Maps4 tm, int H, int W, const float* __restrict__ img1,
+ssim_bwd_kernel(const __grid_constant__ Maps4 tm, int H, int W, int planes, const float* __restrict__ img1,
                 const float* __restrict__ img2, const float* __restrict__ dL_dmap, const float* __restrict__ dm_dmu1,
                 const float* __restrict__ dm_dsigma1_sq, const float* __restrict__ dm_dsigma12,
                 float* __restrict__ dL_dimg1) {
   extern __shared__ __align__(128) unsigned char ssim_smem[];
   BwdSmem& S = *reinterpret_cast<BwdSmem*>(ssim_smem);
   const int t = threadIdx.x;
-  const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH, plane = blockIdx.z;
-  const size_t poff = (size_t)plane * H * W;
+  TileIter it;
+  it.tiles_x = (W + TW - 1) / TW; it.tiles_y = (H + TH - 1) / TH; it.ntiles = it.tiles_x * it.tiles_y * planes;
 
+  auto request = [&](int tile, int stage) {      // thread 0 only
+    int bx, by, pl;
+    it.decode(tile, bx, by, pl);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    mbar_expect_tx(&S.bar[stage], 4u * BOX_FLOATS * sizeof(float));
+#pragma unroll
+    for (int k = 0; k < 4; k++) tma_load_box(S.box[stage][k], &tm.m[k], bx - HX, by - HALO, pl, &S.bar[stage]);
+  };
   if (USE_TMA) {
     if (t == 0) {
-      mbar_init(&S.bar, 1);
+      mbar_init(&S.bar[0], 1); mbar_init(&S.bar[1], 1);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-      mbar_expect_tx(&S.bar, 4u * BOX_FLOATS * sizeof(float));
-#pragma unroll
-      for (int k = 0; k < 4; k++) tma_load_box(S.box[k], &tm.m[k], x0 - HX, y0 - HALO, plane, &S.bar);
+      if ((int)blockIdx.x < it.ntiles) request(blockIdx.x, 0);
     }
     __syncthreads();
-    mbar_wait(&S.bar, 0);
+  }
+
+  int iter = 0;
+  for (int tile = blockIdx.x; tile < it.ntiles; tile += gridDim.x, iter++) {
+  constexpr int stage = 0;
+  int x0, y0, plane;
+  it.decode(tile, x0, y0, plane);
+  const size_t poff = (size_t)plane * H * W;
+  if (USE_TMA) {
+    mbar_wait(&S.bar[0], (unsigned)iter & 1u);
   } else {
-    load_box_generic(S.box[0], dL_dmap + poff, x0 - HX, y0 - HALO, W, H);
-    load_box_generic(S.box[1], dm_dmu1 + poff, x0 - HX, y0 - HALO, W, H);
-    load_box_generic(S.box[2], dm_dsigma1_sq + poff, x0 - HX, y0 - HALO, W, H);
-    load_box_generic(S.box[3], dm_dsigma12 + poff, x0 - HX, y0 - HALO, W, H);
+    load_box_generic(S.box[stage][0], dL_dmap + poff, x0 - HX, y0 - HALO, W, H);
+    load_box_generic(S.box[stage][1], dm_dmu1 + poff, x0 - HX, y0 - HALO, W, H);
+    load_box_generic(S.box[stage][2], dm_dsigma1_sq + poff, x0 - HX, y0 - HALO, W, H);
+    load_box_generic(S.box[stage][3], dm_dsigma12 + poff, x0 - HX, y0 - HALO, W, H);
     __syncthreads();
   }
 
@@ -289,10 +340,10 @@ ssim_bwd_kernel(const __grid_constant__ Maps4 tm, int H, int W, const float* __r
     float Q[14];
 #pragma unroll
     for (int q = 0; q < 5; q++) {             // box columns 4xg .. 4xg+19, of which 4xg+3 .. 4xg+16 are used
-      const float4 g = *reinterpret_cast<const float4*>(&S.box[0][row * BOX_W + 4 * xg + 4 * q]);
-      const float4 a = *reinterpret_cast<const float4*>(&S.box[1][row * BOX_W + 4 * xg + 4 * q]);
-      const float4 b = *reinterpret_cast<const float4*>(&S.box[2][row * BOX_W + 4 * xg + 4 * q]);
-      const float4 c = *reinterpret_cast<const float4*>(&S.box[3][row * BOX_W + 4 * xg + 4 * q]);
+      const float4 g = *reinterpret_cast<const float4*>(&S.box[stage][0][row * BOX_W + 4 * xg + 4 * q]);
+      const float4 a = *reinterpret_cast<const float4*>(&S.box[stage][1][row * BOX_W + 4 * xg + 4 * q]);
+      const float4 b = *reinterpret_cast<const float4*>(&S.box[stage][2][row * BOX_W + 4 * xg + 4 * q]);
+      const float4 c = *reinterpret_cast<const float4*>(&S.box[stage][3][row * BOX_W + 4 * xg + 4 * q]);
       const float gg[4] = {g.x, g.y, g.z, g.w}, aa[4] = {a.x, a.y, a.z, a.w}, bb[4] = {b.x, b.y, b.z, b.w},
                   cc[4] = {c.x, c.y, c.z, c.w};
 #pragma unroll
@@ -323,6 +374,7 @@ ssim_bwd_kernel(const __grid_constant__ Maps4 tm, int H, int W, const float* __r
     *reinterpret_cast<float4*>(&S.h2[row][4 * xg]) = make_float4(o2[0], o2[1], o2[2], o2[3]);
   }
   __syncthreads();
+  if (USE_TMA && t == 0 && tile + (int)gridDim.x < it.ntiles) request(tile + gridDim.x, 0);   // boxes are free again
 
   const int cg = t & 31, rg = t >> 5;
   const int lx = 2 * cg, ly = 4 * rg;
@@ -368,6 +420,8 @@ ssim_bwd_kernel(const __grid_constant__ Maps4 tm, int H, int W, const float* __r
         if (gx + c < W) dL_dimg1[o + c] = s0[c] + (2.f * img1[o + c]) * s1[c] + img2[o + c] * v2[r][c];
     }
   }
+  __syncthreads();      // the vertical pass is done with h01/h2 before the next tile's horizontal pass rewrites them
+  }   // tile loop
 }
 
 // ---- tensor maps ----------------------------------------------------------------------------------------------
@@ -403,6 +457,15 @@ bool tma_enabled() {   // SFGS_SSIM_TMA=0 forces the cooperative tile load (debu
 }
 bool tma_ok(const void* p, int W) { return tma_enabled() && (W % 4) == 0 && (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
+int sm_count() {
+  static int n[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) return 148;
+  if (n[dev] == 0) { int v = 148; cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev); n[dev] = v > 0 ? v : 148; }
+  return n[dev];
+}
+
 template <typename K>
 void opt_in(K kernel, size_t smem) { cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); }
 
@@ -423,7 +486,8 @@ int sfgs_fusedssim_forward(float C1, float C2, int B, int CH, int H, int W, cons
   for (const void* p : {(const void*)ssim_map, (const void*)dm_dmu1, (const void*)dm_dsigma1_sq, (const void*)dm_dsigma12})
     if (p && (reinterpret_cast<uintptr_t>(p) & 7)) return sfgs_set_error(SFGS_E_BADARG, "fusedssim_forward: outputs must be 8-byte aligned", 0);
   const int planes = B * CH;
-  dim3 grid((W + TW - 1) / TW, (H + TH - 1) / TH, planes);
+  const long long ntiles = (long long)((W + TW - 1) / TW) * ((H + TH - 1) / TH) * planes;
+  const int grid = (int)(ntiles < 2LL * sm_count() ? ntiles : 2LL * sm_count());   // persistent: two CTAs per SM
   Maps4 tm = {};
   const bool use_tma = tma_ok(img1, W) && tma_ok(img2, W) && make_map(&tm.m[0], img1, planes, H, W) &&
                        make_map(&tm.m[1], img2, planes, H, W);
@@ -435,7 +499,7 @@ int sfgs_fusedssim_forward(float C1, float C2, int B, int CH, int H, int W, cons
   cudaStream_t st = (cudaStream_t)stream;
   SFGS_COUNT_LAUNCH();
 #define SSIM_FWD(TR, TM) ssim_fwd_kernel<TR, TM><<<grid, SSIM_THREADS, sizeof(FwdSmem), st>>>( \
-      tm, H, W, C1, C2, img1, img2, ssim_map, dm_dmu1, dm_dsigma1_sq, dm_dsigma12)
+      tm, H, W, planes, C1, C2, img1, img2, ssim_map, dm_dmu1, dm_dsigma1_sq, dm_dsigma12)
   if (train) { if (use_tma) SSIM_FWD(true, true); else SSIM_FWD(true, false); }
   else { if (use_tma) SSIM_FWD(false, true); else SSIM_FWD(false, false); }
 #undef SSIM_FWD
@@ -454,7 +518,8 @@ int sfgs_fusedssim_backward(float C1, float C2, int B, int CH, int H, int W, con
   for (const void* p : {(const void*)img1, (const void*)img2, (const void*)dL_dimg1})
     if (reinterpret_cast<uintptr_t>(p) & 7) return sfgs_set_error(SFGS_E_BADARG, "fusedssim_backward: images must be 8-byte aligned", 0);
   const int planes = B * CH;
-  dim3 grid((W + TW - 1) / TW, (H + TH - 1) / TH, planes);
+  const long long ntiles = (long long)((W + TW - 1) / TW) * ((H + TH - 1) / TH) * planes;
+  const int grid = (int)(ntiles < 2LL * sm_count() ? ntiles : 2LL * sm_count());   // persistent: two CTAs per SM
   Maps4 tm = {};
   const float* src[4] = {dL_dmap, dm_dmu1, dm_dsigma1_sq, dm_dsigma12};
   bool use_tma = true;
@@ -464,11 +529,11 @@ int sfgs_fusedssim_backward(float C1, float C2, int B, int CH, int H, int W, con
   cudaStream_t st = (cudaStream_t)stream;
   SFGS_COUNT_LAUNCH();
   if (use_tma)
-    ssim_bwd_kernel<true><<<grid, SSIM_THREADS, sizeof(BwdSmem), st>>>(tm, H, W, img1, img2, dL_dmap, dm_dmu1, dm_dsigma1_sq,
-                                                                     dm_dsigma12, dL_dimg1);
+    ssim_bwd_kernel<true><<<grid, SSIM_THREADS, sizeof(BwdSmem), st>>>(tm, H, W, planes, img1, img2, dL_dmap, dm_dmu1,
+                                                                     dm_dsigma1_sq, dm_dsigma12, dL_dimg1);
   else
-    ssim_bwd_kernel<false><<<grid, SSIM_THREADS, sizeof(BwdSmem), st>>>(tm, H, W, img1, img2, dL_dmap, dm_dmu1, dm_dsigma1_sq,
-                                                                      dm_dsigma12, dL_dimg1);
+    ssim_bwd_kernel<false><<<grid, SSIM_THREADS, sizeof(BwdSmem), st>>>(tm, H, W, planes, img1, img2, dL_dmap, dm_dmu1,
+                                                                      dm_dsigma1_sq, dm_dsigma12, dL_dimg1);
   const cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? SFGS_OK : sfgs_set_error(SFGS_E_CUDA, "fusedssim_backward", (int)e);
 }
