@@ -604,6 +604,15 @@ def main():
                 tilerows.append({"label": label, "error": f"{type(exc).__name__}: {exc}"[:300]})
         d = make_inputs(scene, cam, dev)
 
+    # ---- IDU render set sharded by view (SURVEY 8f rank 4 / BASELINE configs[4], rasterizer side): every rank takes part
+    renderset = None
+    if kind == "ours" and not args.no_extras:
+        try:
+            from sfgs import renderset as RS
+            renderset = RS.run_renderset(P_GAUSS, rank, world, dev)
+        except Exception as exc:  # noqa: BLE001
+            renderset = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -627,6 +636,8 @@ def main():
                          "shim": "reference CudaRasterizer::Rasterizer forward/backward behind the ctypes shim"}[kind]
     if tilerows is not None:
         out["tilerows"] = tilerows
+    if renderset is not None:
+        out["renderset"] = renderset
     if kind == "ours":
         l0 = native.lib().sfgs_launch_count()
         f, _ = step()

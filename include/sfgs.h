@@ -253,6 +253,16 @@ int sfgs_appearance_forward(int P, int D, int M, const float* features, const fl
                             const float* W3, const float* b3, const float* means3D, const float* campos,
                             float* colors, void* stream);
 
+/* ---- 3D smoothing filter -----------------------------
+ * GaussianModel.compute_3D_filter (scene/gaussian_model.py:254-308) as one pass over the Gaussians: for every Gaussian
+ * the smallest view depth over the cameras that see it (depth > 0.2, projection inside the image grown by 15 %), the
+ * largest such depth for Gaussians no camera sees, divided by the largest focal length, times sqrt(0.2).  float64
+ * arithmetic like the reference.  cams: DEVICE array [C][18] doubles per camera = R[9] (camera.R, row-major, used as
+ * xyz @ R), T[3], focal_x, focal_y, cx_ori, cy_ori (principal point in pixels: c/2*size + size/2), width, height.
+ * filter_3D: [P] doubles out; scratch8: 8 bytes of device scratch. */
+int sfgs_compute_3d_filter(int P, const float* xyz, int C, const double* cams, double focal_max, double* filter_3D,
+                           void* scratch8, void* stream);
+
 /* ---- fused SSIM ---------------------------------------------------------- */
 int sfgs_fusedssim_forward(float C1, float C2, int B, int CH, int H, int W,
                            const float* img1, const float* img2, int train,

@@ -243,6 +243,23 @@ def test_long_tile_lists_use_both_sort_paths(cuda_device):
     assert torch.equal(oi["point_list"], ri["point_list"]) and torch.equal(oi["ranges"], ri["ranges"])
     assert torch.equal(oi["n_contrib"], ri["n_contrib"])
     assert (ours["color"] - ref["color"]).abs().max().item() <= IMG_ATOL
+    # the oversized-tile path (single-CTA radix sort through global memory) must stay in the same league as the
+    # reference's global radix sort on the same frame, not fall off a cliff
+    def timed(fn):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize(dev)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(10):
+            fn()
+        b.record()
+        torch.cuda.synchronize(dev)
+        return a.elapsed_time(b) / 10
+    t_ours = timed(lambda: Hh.run_ours_forward(d, cam, 3, bg_t))
+    t_ref = timed(lambda: Hh.run_ref_forward(d, cam, 3, bg_t))
+    print(f"\n[long tile lists] longest {longest}: forward {t_ours:.3f} ms (reference {t_ref:.3f} ms)")
+    assert t_ours <= 1.5 * t_ref + 0.2, (t_ours, t_ref)
 
 
 def test_full_size_properties(cuda_device):

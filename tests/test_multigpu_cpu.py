@@ -81,3 +81,43 @@ def test_gather_and_reduce_world2_gloo():
     assert sorted(r[0] for r in res) == [0, 1]
     assert all(r[1] for r in res), "padded band all_gather did not reassemble the frame"
     assert all(r[2] for r in res), "flat gradient all_reduce mismatch"
+
+
+def _renderset_worker(rank, world, port, q):
+    import os
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    import torch
+    import torch.distributed as dist
+    from sfgs import renderset as RS
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    n_views = 7
+    cuts = RS.partition_views(n_views, world)
+    H, W = 4, 6
+    mine = range(cuts[rank], cuts[rank + 1])
+    color = torch.stack([torch.full((3, H, W), v, dtype=torch.uint8) for v in mine]) if len(mine) else torch.empty((0, 3, H, W), dtype=torch.uint8)
+    depth = torch.stack([torch.full((1, H, W), float(v) + 0.5) for v in mine]) if len(mine) else torch.empty((0, 1, H, W))
+    c, z = RS.gather_views(color, depth, cuts)
+    ok = c.shape == (n_views, 3, H, W) and all(int(c[v, 0, 0, 0]) == v and abs(float(z[v, 0, 0, 0]) - v - 0.5) < 1e-6 for v in range(n_views))
+    q.put((rank, ok, cuts))
+    dist.destroy_process_group()
+
+
+def test_renderset_view_sharding_gathers_every_view_in_order():
+    """the IDU render set shards by view; host logic (partition, padded gather, reassembly) on gloo."""
+    import torch.multiprocessing as mp
+    from sfgs import renderset as RS
+    assert RS.partition_views(108, 8) == [0, 14, 28, 42, 56, 69, 82, 95, 108]
+    assert RS.partition_views(3, 4) == [0, 1, 2, 3, 3]
+    assert len(RS.idu_grid_targets()) == 9
+    cams = RS.idu_orbit_cameras(RS.idu_grid_targets(), 85.0, 300.0, num_cams=6, num_samples=2, size=64)
+    assert len(cams) == 108 and cams[0].width == 64 and cams[0] is cams[1] and cams[0] is not cams[2]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_renderset_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(ok for _, ok, _ in res), res
