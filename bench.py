@@ -414,7 +414,7 @@ def frame_record(name, impl_kind, dev, steps):
     else:
         R, radii = int(f[0]), f[5]
     rec = {"name": name, "P": P, "extent": round(extent, 2), "camera": camname, "value": round(cam.width * cam.height / med / 1e3, 2),
-           "unit": "Mpix/s", "ms_per_step": round(med, 4), "ms_min": round(min(ms), 4), "steps": steps,
+           "unit": "Mpix/s", "ms_per_step": round(med, 4), "ms_min": round(min(ms), 4), "ms_all": [round(m, 3) for m in ms], "steps": steps,
            "V": int((radii > 0).sum().item()), "R": R}
     if impl_kind == "ours":
         per_stage = {}

@@ -14,17 +14,21 @@
 // The per-camera embedding `aemb` is the same vector for every Gaussian, so its 32 columns of W1 fold into the bias
 // (b1' = b1 + W1[:, 27:] aemb, computed once per CTA) and layer 1 contracts over K = 27 (padded to 32).
 //
-// Tensor cores: a CTA owns a tile of 128 Gaussians = the M = 128 rows of three tcgen05.mma (kind::f16, bf16 operands,
-// fp32 accumulate) GEMMs: [128x32]x[32x128], [128x128]x[128x128], [128x128]x[128x16].  Weights are converted to bf16
+// Tensor cores: a CTA owns a tile of 128 Gaussians = the M = 128 rows of three tcgen05.mma (kind::f16, split-bf16
+// operands, fp32 accumulate) GEMMs: [128x32]x[32x128], [128x128]x[128x128], [128x128]x[128x16].  Weights are converted to bf16
 // once per CTA and stay in shared memory in the canonical K-major no-swizzle core-matrix layout (8 rows x 16 bytes per
 // core; SBO = 128 B between 8-row groups, LBO = bytes between the two 16-byte K chunks of one MMA); activations never
 // leave the SM: thread m packs row m of the A operand into the same layout, one elected thread issues the MMAs, the
 // fp32 accumulator lives in TMEM (128 lanes x 128 columns) and comes back with tcgen05.ld (lane m -> thread m) for the
 // bias + ReLU + bf16 pack of the next layer.  CTAs are persistent over tiles.
 //
-// Precision: bf16 inputs / weights, fp32 accumulation, everything after the MLP in fp32.  The MLP output is scaled by
-// 0.01 before it touches the colour, so bf16's 2^-9 relative rounding shows up as ~1e-5 in `offset` / `mul`; the
-// parity test holds the colours to 5e-4 absolute against the reference's own modules evaluated in float32.
+// Precision: the multiplier head of a trained model is O(1) (h ~ 100 before the x0.01), so plain bf16 operands
+// (2^-9 relative) would leave ~1e-2 in the colours (measured on the golden vectors: 8e-3).  Every operand is therefore
+// carried as TWO bf16 values, x = hi + lo with lo = bf16(x - hi) (16 mantissa bits together), and every product is
+// three tensor-core MMAs into the same fp32 accumulator:  A W ~= Ah Wh + Ah Wl + Al Wh  (the dropped Al Wl term is
+// 2^-18 relative).  The GEMMs stay on tcgen05 at 3x the MMA count — still far below the kernel's HBM time — and the
+// colours agree with the reference's float32 modules to 1e-4 (tests/test_appearance.py).  Everything after the MLP is
+// float32.
 #include <cuda_bf16.h>
 #include "sfgs_common.cuh"
 
@@ -38,11 +42,11 @@ constexpr int AP_N3 = 16;            // 6 outputs padded to the smallest N of an
 constexpr int AP_G = 24, AP_E = 32;  // Fourier features per Gaussian, per-camera embedding size
 constexpr int AP_TMEM_COLS = 128;
 
-struct alignas(128) ApSmem {
-  __nv_bfloat16 A[AP_H / 8][AP_M / 8][8][8];     // 32 KB  activations, K-major cores: [k chunk][row group][row][8 k]
-  __nv_bfloat16 W1[AP_K1 / 8][AP_H / 8][8][8];   //  8 KB  [k chunk][n group][n][8 k]
-  __nv_bfloat16 W2[AP_H / 8][AP_H / 8][8][8];    // 32 KB
-  __nv_bfloat16 W3[AP_H / 8][AP_N3 / 8][8][8];   //  4 KB
+struct alignas(128) ApSmem {                       // [2] = {hi, lo} halves of the split operands
+  __nv_bfloat16 A[2][AP_H / 8][AP_M / 8][8][8];     // 64 KB  activations, K-major cores: [k chunk][row group][row][8 k]
+  __nv_bfloat16 W1[2][AP_K1 / 8][AP_H / 8][8][8];   // 16 KB  [k chunk][n group][n][8 k]
+  __nv_bfloat16 W2[2][AP_H / 8][AP_H / 8][8][8];    // 64 KB
+  __nv_bfloat16 W3[2][AP_H / 8][AP_N3 / 8][8][8];   //  8 KB
   float b1[AP_H], b2[AP_H], b3[8];
   unsigned long long bar;
   uint32_t tmem_base;
@@ -107,8 +111,21 @@ __device__ __forceinline__ uint4 pack8(const float* v) {
   return make_uint4(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b), *reinterpret_cast<uint32_t*>(&c),
                     *reinterpret_cast<uint32_t*>(&d));
 }
+// x = hi + lo: hi = bf16(x), lo = bf16(x - hi)
+__device__ __forceinline__ void split8(const float* v, uint4& hi, uint4& lo) {
+  float r[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) r[i] = v[i] - __bfloat162float(__float2bfloat16(v[i]));
+  hi = pack8(v);
+  lo = pack8(r);
+}
+__device__ __forceinline__ void split_store(__nv_bfloat16* hi, __nv_bfloat16* lo, float x) {
+  const __nv_bfloat16 h = __float2bfloat16(x);
+  *hi = h;
+  *lo = __float2bfloat16(x - __bfloat162float(h));
+}
 
-__global__ void __launch_bounds__(AP_THREADS, 2)
+__global__ void __launch_bounds__(AP_THREADS, 1)
 appearance_fwd_kernel(int P, int D, const float* __restrict__ features /*[P,16,3]*/, const float* __restrict__ gemb /*[P,24]*/,
                       const float* __restrict__ aemb /*[32]*/, const float* __restrict__ W1 /*[128,59]*/,
                       const float* __restrict__ b1, const float* __restrict__ W2 /*[128,128]*/, const float* __restrict__ b2,
@@ -131,15 +148,15 @@ appearance_fwd_kernel(int P, int D, const float* __restrict__ features /*[P,16,3
   }
   for (int i = t; i < AP_H * AP_K1; i += AP_THREADS) {          // W1[n][k], k < 27 (colour 3 + Fourier 24), zero padded
     const int n = i / AP_K1, k = i - n * AP_K1;
-    S.W1[k >> 3][n >> 3][n & 7][k & 7] = __float2bfloat16(k < 3 + AP_G ? W1[n * IN + k] : 0.f);
+    split_store(&S.W1[0][k >> 3][n >> 3][n & 7][k & 7], &S.W1[1][k >> 3][n >> 3][n & 7][k & 7], k < 3 + AP_G ? W1[n * IN + k] : 0.f);
   }
   for (int i = t; i < AP_H * AP_H; i += AP_THREADS) {
     const int n = i / AP_H, k = i - n * AP_H;
-    S.W2[k >> 3][n >> 3][n & 7][k & 7] = __float2bfloat16(W2[i]);
+    split_store(&S.W2[0][k >> 3][n >> 3][n & 7][k & 7], &S.W2[1][k >> 3][n >> 3][n & 7][k & 7], W2[i]);
   }
   for (int i = t; i < AP_N3 * AP_H; i += AP_THREADS) {
     const int n = i / AP_H, k = i - n * AP_H;
-    S.W3[k >> 3][n >> 3][n & 7][k & 7] = __float2bfloat16(n < 6 ? W3[n * AP_H + k] : 0.f);
+    split_store(&S.W3[0][k >> 3][n >> 3][n & 7][k & 7], &S.W3[1][k >> 3][n >> 3][n & 7][k & 7], n < 6 ? W3[n * AP_H + k] : 0.f);
   }
   {
     float acc = b1[t];                                           // AP_THREADS == AP_H
@@ -176,8 +193,12 @@ appearance_fwd_kernel(int P, int D, const float* __restrict__ features /*[P,16,3
 #pragma unroll
       for (int k = 3 + AP_G; k < AP_K1; k++) in[k] = 0.f;
 #pragma unroll
-      for (int kc = 0; kc < AP_K1 / 8; kc++)
-        *reinterpret_cast<uint4*>(&S.A[kc][t >> 3][t & 7][0]) = pack8(in + 8 * kc);
+      for (int kc = 0; kc < AP_K1 / 8; kc++) {
+        uint4 hi, lo;
+        split8(in + 8 * kc, hi, lo);
+        *reinterpret_cast<uint4*>(&S.A[0][kc][t >> 3][t & 7][0]) = hi;
+        *reinterpret_cast<uint4*>(&S.A[1][kc][t >> 3][t & 7][0]) = lo;
+      }
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the MMA's async proxy
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -186,9 +207,13 @@ appearance_fwd_kernel(int P, int D, const float* __restrict__ features /*[P,16,3
     if (t == 0) {
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
-      for (int ks = 0; ks < AP_K1 / 16; ks++)
-        umma_bf16(tmem, smem_desc(&S.A[2 * ks][0][0][0], 2048, 128), smem_desc(&S.W1[2 * ks][0][0][0], 2048, 128),
-                  instr_desc(AP_M, AP_H), ks > 0);
+      for (int ks = 0; ks < AP_K1 / 16; ks++) {
+        const uint64_t ah = smem_desc(&S.A[0][2 * ks][0][0][0], 2048, 128), al = smem_desc(&S.A[1][2 * ks][0][0][0], 2048, 128);
+        const uint64_t wh = smem_desc(&S.W1[0][2 * ks][0][0][0], 2048, 128), wl = smem_desc(&S.W1[1][2 * ks][0][0][0], 2048, 128);
+        umma_bf16(tmem, ah, wh, instr_desc(AP_M, AP_H), ks > 0);
+        umma_bf16(tmem, ah, wl, instr_desc(AP_M, AP_H), 1);
+        umma_bf16(tmem, al, wh, instr_desc(AP_M, AP_H), 1);
+      }
       umma_commit(&S.bar);
     }
     mbar_wait(&S.bar, phase); phase ^= 1;
@@ -201,7 +226,12 @@ appearance_fwd_kernel(int P, int D, const float* __restrict__ features /*[P,16,3
 #pragma unroll
       for (int i = 0; i < 32; i++) v[i] = fmaxf(v[i] + S.b1[c0 + i], 0.f);
 #pragma unroll
-      for (int q = 0; q < 4; q++) *reinterpret_cast<uint4*>(&S.A[(c0 >> 3) + q][t >> 3][t & 7][0]) = pack8(v + 8 * q);
+      for (int q = 0; q < 4; q++) {
+        uint4 hi, lo;
+        split8(v + 8 * q, hi, lo);
+        *reinterpret_cast<uint4*>(&S.A[0][(c0 >> 3) + q][t >> 3][t & 7][0]) = hi;
+        *reinterpret_cast<uint4*>(&S.A[1][(c0 >> 3) + q][t >> 3][t & 7][0]) = lo;
+      }
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -210,9 +240,13 @@ appearance_fwd_kernel(int P, int D, const float* __restrict__ features /*[P,16,3
     if (t == 0) {
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
-      for (int ks = 0; ks < AP_H / 16; ks++)
-        umma_bf16(tmem, smem_desc(&S.A[2 * ks][0][0][0], 2048, 128), smem_desc(&S.W2[2 * ks][0][0][0], 2048, 128),
-                  instr_desc(AP_M, AP_H), ks > 0);
+      for (int ks = 0; ks < AP_H / 16; ks++) {
+        const uint64_t ah = smem_desc(&S.A[0][2 * ks][0][0][0], 2048, 128), al = smem_desc(&S.A[1][2 * ks][0][0][0], 2048, 128);
+        const uint64_t wh = smem_desc(&S.W2[0][2 * ks][0][0][0], 2048, 128), wl = smem_desc(&S.W2[1][2 * ks][0][0][0], 2048, 128);
+        umma_bf16(tmem, ah, wh, instr_desc(AP_M, AP_H), ks > 0);
+        umma_bf16(tmem, ah, wl, instr_desc(AP_M, AP_H), 1);
+        umma_bf16(tmem, al, wh, instr_desc(AP_M, AP_H), 1);
+      }
       umma_commit(&S.bar);
     }
     mbar_wait(&S.bar, phase); phase ^= 1;
@@ -224,7 +258,12 @@ appearance_fwd_kernel(int P, int D, const float* __restrict__ features /*[P,16,3
 #pragma unroll
       for (int i = 0; i < 32; i++) v[i] = fmaxf(v[i] + S.b2[c0 + i], 0.f);
 #pragma unroll
-      for (int q = 0; q < 4; q++) *reinterpret_cast<uint4*>(&S.A[(c0 >> 3) + q][t >> 3][t & 7][0]) = pack8(v + 8 * q);
+      for (int q = 0; q < 4; q++) {
+        uint4 hi, lo;
+        split8(v + 8 * q, hi, lo);
+        *reinterpret_cast<uint4*>(&S.A[0][(c0 >> 3) + q][t >> 3][t & 7][0]) = hi;
+        *reinterpret_cast<uint4*>(&S.A[1][(c0 >> 3) + q][t >> 3][t & 7][0]) = lo;
+      }
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -233,9 +272,13 @@ appearance_fwd_kernel(int P, int D, const float* __restrict__ features /*[P,16,3
     if (t == 0) {
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
-      for (int ks = 0; ks < AP_H / 16; ks++)
-        umma_bf16(tmem, smem_desc(&S.A[2 * ks][0][0][0], 2048, 128), smem_desc(&S.W3[2 * ks][0][0][0], 256, 128),
-                  instr_desc(AP_M, AP_N3), ks > 0);
+      for (int ks = 0; ks < AP_H / 16; ks++) {
+        const uint64_t ah = smem_desc(&S.A[0][2 * ks][0][0][0], 2048, 128), al = smem_desc(&S.A[1][2 * ks][0][0][0], 2048, 128);
+        const uint64_t wh = smem_desc(&S.W3[0][2 * ks][0][0][0], 256, 128), wl = smem_desc(&S.W3[1][2 * ks][0][0][0], 256, 128);
+        umma_bf16(tmem, ah, wh, instr_desc(AP_M, AP_N3), ks > 0);
+        umma_bf16(tmem, ah, wl, instr_desc(AP_M, AP_N3), 1);
+        umma_bf16(tmem, al, wh, instr_desc(AP_M, AP_N3), 1);
+      }
       umma_commit(&S.bar);
     }
     mbar_wait(&S.bar, phase); phase ^= 1;
@@ -318,7 +361,7 @@ extern "C" int sfgs_appearance_forward(int P, int D, int M, const float* feature
   }
   const int nsm = (dev >= 0 && dev < 64 && sms[dev] > 0) ? sms[dev] : 148;
   const int ntiles = (P + AP_M - 1) / AP_M;
-  const int grid = ntiles < 2 * nsm ? ntiles : 2 * nsm;      // persistent: two CTAs per SM (shared memory and TMEM allow it)
+  const int grid = ntiles < nsm ? ntiles : nsm;              // persistent: one CTA per SM (154 KB of operands in shared memory)
   SFGS_COUNT_LAUNCH();
   appearance_fwd_kernel<<<grid, AP_THREADS, sizeof(ApSmem), (cudaStream_t)stream>>>(P, D, features, gemb, aemb, W1, b1, W2, b2,
                                                                                   W3, b3, means3D, campos, colors);

@@ -239,12 +239,31 @@ preprocess_kernel(int P, int D, int M,
                     vm[8] * vm[8] + vm[9] * vm[9] + vm[10] * vm[10];
   const float jw2 = (focal_x * focal_x * (1.f + limx * limx) + focal_y * focal_y * (1.f + limy * limy)) * wf2;
   unsigned cand_bits = 0;          // bit j: Gaussian base + j*256 + tid is a candidate
-#pragma unroll 1
+  // every load of the four Gaussians is issued before anything is computed: one DRAM round trip per thread instead of
+  // eight dependent ones (the test is latency-bound; the few bytes fetched for Gaussians behind the camera are cheaper
+  // than a second trip)
+  float3 pos4[4], scl4[4];
+  float4 rot4[4];
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    const int i = base + j * PRE_THREADS + tid;
+    const size_t ii = (size_t)(i < P ? i : P - 1);
+    pos4[j] = make_float3(means3D[3 * ii], means3D[3 * ii + 1], means3D[3 * ii + 2]);
+    if (cov3D_precomp != nullptr) {
+      const float* c = cov3D_precomp + 6 * ii;
+      scl4[j] = make_float3(c[0], c[3], c[5]);
+      rot4[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    } else {
+      scl4[j] = make_float3(scales[3 * ii], scales[3 * ii + 1], scales[3 * ii + 2]);
+      rot4[j] = *reinterpret_cast<const float4*>(rotations + 4 * ii);
+    }
+  }
+#pragma unroll
   for (int j = 0; j < 4; j++) {
     const int i = base + j * PRE_THREADS + tid;
     bool cand_j = false;
     if (i < P) {
-      const float px = means3D[3 * (size_t)i], py = means3D[3 * (size_t)i + 1], pz = means3D[3 * (size_t)i + 2];
+      const float px = pos4[j].x, py = pos4[j].y, pz = pos4[j].z;
       const float view_z = vm[2] * px + vm[6] * py + vm[10] * pz + vm[14];
       if (prefiltered && !(view_z > 0.2f)) hdr[HDR_PREFILTER] = 1u;     // the reference traps (auxiliary.h:157-161)
       if (view_z > 0.199f) {                                            // 0.2 with a margin: the exact test follows
@@ -255,11 +274,10 @@ preprocess_kernel(int P, int D, int M,
         const float pix_x = ndc_to_pix(hx * p_w, W), pix_y = ndc_to_pix(hy * p_w, H);
         float trace_sigma;
         if (cov3D_precomp != nullptr) {
-          const float* c = cov3D_precomp + 6 * (size_t)i;
-          trace_sigma = c[0] + c[3] + c[5];
+          trace_sigma = scl4[j].x + scl4[j].y + scl4[j].z;
         } else {
-          const float sx = scales[3 * (size_t)i], sy = scales[3 * (size_t)i + 1], sz = scales[3 * (size_t)i + 2];
-          const float4 q = *reinterpret_cast<const float4*>(rotations + 4 * (size_t)i);
+          const float sx = scl4[j].x, sy = scl4[j].y, sz = scl4[j].z;
+          const float4 q = rot4[j];
           float R[3][3];
           rot_from_quat(q.x, q.y, q.z, q.w, R);
           // trace(Sigma) = sum_r (mod s_r)^2 sum_c R[c][r]^2

@@ -223,18 +223,21 @@ def run_tilerows(P, extent, rank, world, dev, steps, warmup):
             frame_peers = [int(p) for p in fh.buffer_ptrs]
 
             def step_peer():
-                fh.barrier(channel=0)                               # nobody still reads the previous frame
+                # Two device-side barriers per step.  (B) after the forward: every band has landed in every rank's frame
+                # block AND every rank's accumulator slice is clear (it is zeroed before the forward, in stream order
+                # after this rank's previous phase 2).  (C) after the blend adjoint: every rank's reductions have
+                # landed.  No barrier is needed before the forward: a rank passes (C) of the previous step only after
+                # its loss and blend adjoint of that step — the last readers of the previous frame — have completed.
+                acc_sym.zero_()
                 f = R.rasterize_gaussians(d["bg"], d["means3D"], e, d["opacities"], d["scales"], d["rotations"], 1.0,
                                           e, e, e, 0, d["view"], d["proj"], cam.tanfovx, cam.tanfovy, 0.1, H, W,
                                           d["shs"], 3, d["campos"], False, False, tile_rows=band,
                                           out_planes=frame_sym, out_peers=frame_peers)
                 last["R"] = f[0]
-                fh.barrier(channel=1)                               # every band has landed everywhere
+                hdl.barrier(channel=0)                              # (B)
                 full = frame_sym.view(8, H, W)
-                acc_sym.zero_()
-                hdl.barrier(channel=0)                              # every slice is clear before anyone adds
                 bwd(f, phase=1, acc_peers=peers, peer_slice=per)    # reductions land on the owners' slices
-                hdl.barrier(channel=1)                              # every rank's kernel has completed
+                hdl.barrier(channel=1)                              # (C)
                 g = bwd(f, phase=2, acc=acc_sym.view(per, 16), gauss_range=(sl[rank], sl[rank + 1]))
                 return full, g
 

@@ -13,7 +13,7 @@ import pytest
 import torch
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "appearance_ref.npz")
-COLOR_ATOL = 5e-4      # bf16 operands, fp32 accumulation; the MLP output is scaled by 0.01 before it reaches a colour
+COLOR_ATOL = 1e-4      # split-bf16 (hi + lo) tensor-core operands, fp32 accumulation: ~2^-16 relative per product
 
 
 def _load(dev, dtype=torch.float32):
@@ -44,7 +44,7 @@ def test_fused_appearance_kernel_matches_the_reference_modules(cuda_device, deg)
     err = np.abs(got.cpu().numpy().astype(np.float64) - g[f"colors_deg{deg}_f64"])
     assert got.shape == (t["features"].shape[0], 3)
     assert err.max() <= COLOR_ATOL, (deg, float(err.max()))
-    assert err.mean() <= 5e-5, float(err.mean())
+    assert err.mean() <= 1e-5, float(err.mean())
     # zeros where the reference clamps (clamp_min(. + 0.5, 0)) except within the tolerance of the threshold
     ref = g[f"colors_deg{deg}_f64"]
     assert np.all(got.cpu().numpy()[ref == 0.0] <= COLOR_ATOL)
