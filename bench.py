@@ -32,6 +32,8 @@ Extra records in the same line (single-GPU run only; they never change `value`):
                 Mpix/s, V, R and (this library) per-stage times, device-resident leg;
   ssim          fused-ssim forward(train)+backward at 1x3x1080x1920 with the 72N / 84N-byte roofline of SURVEY 8d, this
                 library next to the reference's compiled kernel (when oracle/_ref has it);
+  train_loop    a bounded sample (300 iterations) of the BASELINE configs[2] Stage-1 loop, it/s, either arm with its own packages;
+  next_ops      (this library) the fused appearance path and compute_3D_filter next to their torch formulations;
   roofline.traffic  dram__bytes_read + dram__bytes_write of the dominant kernel measured in THIS run by an `ncu`
                 subprocess (falls back to profiles/traffic.json and says so in `traffic_source`).
 Multi-GPU: the headline is the "views" mode — ranks render different cameras of the replicated scene (weak scaling, no
@@ -471,6 +473,162 @@ def ssim_record(impl_kind, dev, steps=20):
             "mean_ssim": round(float(m.mean().item()), 6), "grad_abs_max": float(gimg.abs().max().item())}
 
 
+def train_loop_record(kind, dev, iters=300):
+    """BASELINE configs[2] shape — the per-iteration work of train.py Stage 1 (train.py:195-260) around the rasterizer:
+    activations -> render one of 8 orbit views at 1920x1080 -> 0.8 L1 + 0.2 (1 - SSIM) -> backward -> Adam on
+    (xyz, scaling, rotation, opacity, SH) — as a bounded sample of `iters` iterations of the 7000 (synthetic scene and
+    targets; no JAX_068 data here).  ours: the drop-in packages + fused activations; reference: ITS OWN diff_gauss and
+    fused_ssim packages (oracle/_ref) + the torch activations of scene/gaussian_model.py:207-249."""
+    if kind == "ours":
+        import diff_gauss as dg
+        import fused_ssim as fs
+        from sfgs.activations import fused_activations
+    elif kind == "stock":
+        dg, fs = ref_packages()
+        fused_activations = None
+    else:
+        return None
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)  # noqa: E731
+    scene = S.city_scene(P_GAUSS, seed=0, sh_degree=SH_DEGREE)
+    cams = [S.orbit_camera(azimuth_deg=45.0 * k) for k in range(8)]
+    P = scene.P
+    bg = torch.zeros(3, device=dev)
+    sub = torch.zeros(1, device=dev)
+    cam_t = [(c, t(c.viewmatrix), t(c.projmatrix), t(c.campos)) for c in cams]
+    m2d = torch.zeros((P, 3), device=dev, requires_grad=True)
+    base = [t(scene.means3D), t(scene.opacities), t(scene.shs), t(scene.scales), t(scene.rotations)]
+    targets = []
+    with torch.no_grad():
+        for c, view, proj, campos in cam_t:
+            rs = dg.GaussianRasterizationSettings(c.height, c.width, c.tanfovx, c.tanfovy, 0.1, sub, bg, 1.0, view, proj,
+                                                  SH_DEGREE, campos, False, False)
+            targets.append(dg.GaussianRasterizer(rs)(base[0], m2d.detach(), base[1], shs=base[2], scales=base[3],
+                                                     rotations=base[4])[0].clone())
+    rng = np.random.default_rng(1)
+    xyz = t((scene.means3D + rng.normal(0, 0.05, scene.means3D.shape)).astype(np.float32)).requires_grad_(True)
+    scaling = torch.log(t(scene.scales)).requires_grad_(True)
+    rotation = t(scene.rotations).clone().requires_grad_(True)
+    opacity = torch.logit(t(scene.opacities).clamp(1e-4, 1 - 1e-4)).reshape(P, 1).clone().requires_grad_(True)
+    shs = (t(scene.shs) * 0.9).requires_grad_(True)
+    filter_3D = torch.full((P, 1), 0.05, dtype=torch.float64, device=dev)
+    opt = torch.optim.Adam([{"params": [xyz], "lr": 1.6e-4}, {"params": [scaling], "lr": 5e-3},
+                            {"params": [rotation], "lr": 1e-3}, {"params": [opacity], "lr": 5e-2},
+                            {"params": [shs], "lr": 2.5e-3}], eps=1e-15)
+
+    def step(i):
+        cam, view, proj, campos = cam_t[i % len(cam_t)]
+        if fused_activations is not None:
+            op, sc, rot = fused_activations(opacity, scaling, rotation, filter_3D)
+        else:
+            sq = torch.square(torch.exp(scaling))                    # scene/gaussian_model.py:207-249
+            a2 = sq + torch.square(filter_3D)
+            sc = torch.sqrt(a2).float()
+            op = (torch.sigmoid(opacity) * torch.sqrt(sq.prod(dim=1) / a2.prod(dim=1))[..., None]).float()
+            rot = torch.nn.functional.normalize(rotation)
+        rs = dg.GaussianRasterizationSettings(cam.height, cam.width, cam.tanfovx, cam.tanfovy, 0.1, sub, bg, 1.0, view, proj,
+                                              SH_DEGREE, campos, False, False)
+        color = dg.GaussianRasterizer(rs)(xyz, m2d, op, shs=shs, scales=sc, rotations=rot)[0]
+        gt = targets[i % len(targets)]
+        loss = 0.8 * torch.nn.functional.l1_loss(color, gt) + 0.2 * (1.0 - fs.fused_ssim(color[None], gt[None]))
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        opt.step()
+        return loss
+
+    for i in range(10):
+        step(i)
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    first = last = None
+    for i in range(iters):
+        loss = step(i)
+        if i == 0:
+            first = loss.detach()
+        last = loss.detach()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1)
+    return {"workload": f"BASELINE configs[2] shape: {iters} of the 7000 Stage-1 iterations (activations, render 1 of 8 orbit "
+                        "views 1920x1080, 0.8 L1 + 0.2 (1-SSIM), backward, Adam), 1M Gaussians, SH 3, synthetic targets",
+            "iterations": iters, "it_per_s": round(iters / (ms / 1e3), 1), "ms_per_it": round(ms / iters, 3),
+            "loss_first": round(float(first), 5), "loss_last": round(float(last), 5)}
+
+
+def next_ops_record(dev):
+    """SURVEY 8f rows built this round, each next to the torch formulation it replaces (this library only)."""
+    from sfgs import appearance as AP
+    from sfgs import filter3d as F3
+    import types
+    out = {}
+    P = P_GAUSS
+    g = torch.Generator(device="cpu").manual_seed(3)
+    feats = (torch.randn(P, 16, 3, generator=g) * 0.3).to(dev); feats[:, 0] += 0.6
+    gemb = torch.sin(torch.randn(P, 24, generator=g) * 3).to(dev)
+    aemb = (torch.randn(32, generator=g) * 0.5).to(dev)
+    xyz = (torch.randn(P, 3, generator=g) * 80).to(dev)
+    campos = torch.tensor([10.0, -300.0, 120.0], device=dev)
+    lin = [torch.nn.Linear(59, 128), torch.nn.Linear(128, 128), torch.nn.Linear(128, 6)]
+    W = [x.to(dev) for l in lin for x in (l.weight.detach(), l.bias.detach())]
+
+    def timeit(fn, n=10):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize(dev)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(n):
+            fn()
+        b.record()
+        torch.cuda.synchronize(dev)
+        return a.elapsed_time(b) / n
+    with torch.no_grad():
+        t_fused = timeit(lambda: AP.fused_appearance_colors(feats, gemb, aemb, tuple(W), xyz, campos, 3))
+        t_torch = timeit(lambda: AP.reference_colors(feats, gemb, aemb, *W, xyz, campos, 3))
+        err = float((AP.fused_appearance_colors(feats, gemb, aemb, tuple(W), xyz, campos, 3)
+                     - AP.reference_colors(feats, gemb, aemb, *W, xyz, campos, 3)).abs().max())
+    peak, _ = peaks()
+    out["appearance_forward"] = {"P": P, "fused_ms": round(t_fused, 4), "torch_eager_ms": round(t_torch, 4),
+                                 "speedup": round(t_torch / t_fused, 1), "max_abs_diff_vs_torch_f32": err,
+                                 "algorithmic_bytes": 324 * P, "GBps": round(324 * P / t_fused / 1e6, 1),
+                                 "frac_of_hbm_peak": round(324 * P / t_fused / 1e6 / peak, 4),
+                                 "tensor_core_flops": 3 * 2 * P * (32 * 128 + 128 * 128 + 128 * 16),
+                                 "note": "tcgen05 kernel (split-bf16 operands, fp32 accumulate in TMEM) vs the reference's statements in torch"}
+    # compute_3D_filter: 64 cameras
+    rng = np.random.default_rng(2)
+    cams = []
+    for c in range(64):
+        cam = S.orbit_camera(azimuth_deg=float(rng.uniform(0, 360)), elevation_deg=float(rng.uniform(40, 88)), radius=float(rng.uniform(200, 400)))
+        w2c = cam.viewmatrix.T.astype(np.float64)
+        cams.append(types.SimpleNamespace(R=w2c[:3, :3].T.copy(), T=w2c[:3, 3].copy(), focal_x=cam.width / (2 * cam.tanfovx),
+                                          focal_y=cam.height / (2 * cam.tanfovy), cx=0.0, cy=0.0, image_width=cam.width, image_height=cam.height))
+    xyz_city = torch.from_numpy(S.city_scene(P, seed=0).means3D).to(dev)
+
+    def torch_filter():      # the reference's statements (scene/gaussian_model.py:254-308) on the GPU in torch
+        x = xyz_city.double()
+        dist = torch.ones(P, device=dev, dtype=torch.float64) * 1e8
+        valid_pts = torch.zeros(P, device=dev, dtype=torch.bool)
+        fl = 0.0
+        for cam in cams:
+            R = torch.tensor(cam.R, device=dev, dtype=torch.float64); T = torch.tensor(cam.T, device=dev, dtype=torch.float64)
+            xc = x @ R + T[None, :]
+            vd = xc[:, 2] > 0.2
+            z = torch.clamp(xc[:, 2], min=0.001)
+            px = xc[:, 0] / z * cam.focal_x + cam.image_width / 2; py = xc[:, 1] / z * cam.focal_y + cam.image_height / 2
+            ins = (px >= -0.15 * cam.image_width) & (px <= cam.image_width * 1.15) & (py >= -0.15 * cam.image_height) & (py <= 1.15 * cam.image_height)
+            v = vd & ins
+            dist[v] = torch.min(dist[v], z[v]); valid_pts |= v
+            fl = max(fl, cam.focal_x)
+        dist[~valid_pts] = dist[valid_pts].max()
+        return (dist / fl * (0.2 ** 0.5))[..., None]
+    t_f = timeit(lambda: F3.compute_3D_filter(xyz_city, cams), n=5)
+    t_t = timeit(torch_filter, n=2)
+    d = float((F3.compute_3D_filter(xyz_city, cams) - torch_filter()).abs().max())
+    out["compute_3D_filter"] = {"P": P, "cameras": len(cams), "fused_ms": round(t_f, 4), "torch_eager_ms": round(t_t, 3),
+                                "speedup": round(t_t / t_f, 1), "max_abs_diff": d}
+    return out
+
+
 def live_traffic(kernel_regex, timeout_s=240):
     """dram__bytes_read + dram__bytes_write (and issue-slot utilisation) of ONE launch of the dominant kernel, captured in
     this run by an ncu subprocess over tests/gpu_profile_case.py (same scene, camera and cotangents as the timed loop).
@@ -592,7 +750,7 @@ def main():
         del d
         torch.cuda.empty_cache()
         tilerows = []
-        for label, P_t, extent in (("1M", P_GAUSS, 256.0), ("configs3_5M", 5_000_000, 256.0 * 5 ** 0.5), ("dense_5M", 5_000_000, 256.0)):
+        for label, P_t, extent in (("1M", P_GAUSS, 256.0), ("configs3_5M", 5_000_000, 256.0 * 5 ** 0.5)):
             try:
                 tsamp = ClockSampler(local_rank, dev)
                 rec = multigpu.run_tilerows(P_t, extent, rank, world, dev, max(10, steps), warmup)
@@ -696,6 +854,15 @@ def main():
             out["ssim"] = ssim_record(kind, dev)
         except Exception as exc:  # noqa: BLE001
             out["ssim"] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+        try:
+            out["train_loop"] = train_loop_record(kind, dev)
+        except Exception as exc:  # noqa: BLE001
+            out["train_loop"] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+        if kind == "ours":
+            try:
+                out["next_ops"] = next_ops_record(dev)
+            except Exception as exc:  # noqa: BLE001
+                out["next_ops"] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
         if kind == "ours":
             torch.cuda.synchronize(dev)
             lt = live_traffic({"render_bwd": "render_bwd", "render_fwd": "render_fwd"}.get(dom, dom))

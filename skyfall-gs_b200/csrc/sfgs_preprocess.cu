@@ -501,10 +501,8 @@ void sfgs_launch_preprocess(const sfgs_forward_args* a, const GeomLayout& g, con
   if (attr_once.first_use()) {
     cudaFuncSetAttribute(preprocess_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   }
-  // tile-row band of this call: (0, 0) = the whole image; begin == end != 0 = an empty band (nothing is binned)
-  const bool whole = a->tile_row_begin == 0 && a->tile_row_end == 0;
-  const int band0 = whole ? 0 : (a->tile_row_begin < im.tiles_y ? a->tile_row_begin : im.tiles_y);
-  const int band1 = whole ? im.tiles_y : (a->tile_row_end < im.tiles_y ? a->tile_row_end : im.tiles_y);
+  const SfgsBand band = sfgs_band(a->tile_row_begin, a->tile_row_end, im.tiles_y);
+  const int band0 = band.b0, band1 = band.b1;
   SFGS_COUNT_LAUNCH();
   preprocess_kernel<<<blocks, PRE_THREADS, smem, st>>>(
       a->P, a->D, a->M, a->means3D, a->scales, a->scale_modifier, a->rotations, a->opacities, a->shs,

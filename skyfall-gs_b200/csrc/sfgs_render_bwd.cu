@@ -573,8 +573,8 @@ render_bwd_warp_kernel(const uint2* __restrict__ ranges, const char* __restrict_
 
 void sfgs_launch_render_bwd(const sfgs_backward_args* a, const GeomLayout& g, const ImageLayout& im,
                             const BinningLayout& b, float* acc, cudaStream_t st) {
-  const int band0 = a->tile_row_end > a->tile_row_begin ? a->tile_row_begin : 0;
-  const int band1 = a->tile_row_end > a->tile_row_begin ? (a->tile_row_end < im.tiles_y ? a->tile_row_end : im.tiles_y) : im.tiles_y;
+  const SfgsBand band = sfgs_band(a->tile_row_begin, a->tile_row_end, im.tiles_y);
+  const int band0 = band.b0, band1 = band.b1;
   if (band1 <= band0) return;
   dim3 grid(im.tiles_x, band1 - band0, 1);
   const size_t smem = sizeof(BwdSmem);

@@ -36,6 +36,16 @@ def _ptr(t, keep):
     return tc.data_ptr()
 
 
+def _band(tile_rows):
+    """(begin, end) of a tile-row band for the C ABI, where (0, 0) means "whole image": an EMPTY band that happens to
+    start at row 0 (a rank without rows when there are fewer tile rows than ranks) is passed as an empty band past the
+    grid instead."""
+    b0, b1 = int(tile_rows[0]), int(tile_rows[1])
+    if b1 <= b0:
+        return 1 << 20, 1 << 20
+    return b0, b1
+
+
 class _Arena:
     """Allocator callback target: the last tensor handed out is the live buffer."""
 
@@ -128,7 +138,7 @@ def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations,
         a.stream = torch.cuda.current_stream(dev).cuda_stream
         a.capacity_hint = int(capacity_hint)
         if tile_rows is not None:
-            a.tile_row_begin, a.tile_row_end = int(tile_rows[0]), int(tile_rows[1])
+            a.tile_row_begin, a.tile_row_end = _band(tile_rows)
         rendered = N.check(L.sfgs_rasterize_forward(C.byref(a)), "sfgs_rasterize_forward")
     ret = (rendered, out_color, out_depth, out_norm, out_alpha, radii, out_extra,
            geom.tensor, binning.tensor, img.tensor)
@@ -234,7 +244,7 @@ def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rot
         a.debug = int(bool(debug))
         a.stream = torch.cuda.current_stream(dev).cuda_stream
         if tile_rows is not None:
-            a.tile_row_begin, a.tile_row_end = int(tile_rows[0]), int(tile_rows[1])
+            a.tile_row_begin, a.tile_row_end = _band(tile_rows)
         N.check(L.sfgs_rasterize_backward(C.byref(a)), "sfgs_rasterize_backward")
     if phase == 1:
         return acc      # None when the sums went straight to the peers' slices

@@ -665,3 +665,38 @@ def test_alternating_frame_sizes_do_not_rerun_the_forward(cuda_device):
         f = Hh.run_ours_forward(ds[i], cams[i], 3, bg)
         assert f["num_rendered"] == ref_R[i]
     assert N.lib().sfgs_overflow_reruns() == before, "a frame size that had been seen before overflowed its binning estimate"
+
+
+def test_prefiltered_and_empty_band_semantics(cuda_device):
+    """`prefiltered=True` promises that no Gaussian fails the frustum test; the reference traps the kernel when one does
+    (CR/auxiliary.h:157-161) — here the call reports an argument error.  A tile-row band with begin == end != 0 is EMPTY
+    (more ranks than tile rows): nothing is binned or blended, unlike (0, 0), which means the whole image."""
+    from sfgs import native as N
+    from sfgs import rasterizer as R
+    dev = cuda_device
+    e = torch.empty(0, device=dev)
+    bg = torch.zeros(3, device=dev)
+    scene, cam = S.blob_scene(800, seed=3, spread=1.0), S.simple_camera(96, 64)     # camera 8 units away: all in front
+    d = Hh.to_torch(scene, cam, dev)
+    vz = d["means3D"] @ d["viewmatrix"][:3, 2] + d["viewmatrix"][3, 2]
+    assert float(vz.min()) > 0.2
+
+    def fwd(means, prefiltered=False, tile_rows=None):
+        return R.rasterize_gaussians(bg, means, e, d["opacities"], d["scales"], d["rotations"], 1.0, e, e, e, 0,
+                                     d["viewmatrix"], d["projmatrix"], cam.tanfovx, cam.tanfovy, 0.1, cam.height, cam.width,
+                                     d["shs"], 3, d["campos"], prefiltered, False, tile_rows=tile_rows)
+    full = fwd(d["means3D"])
+    # every Gaussian of this scene is in front of the camera: prefiltered=True is legal and changes nothing
+    ok = fwd(d["means3D"], prefiltered=True)
+    assert ok[0] == full[0] and torch.equal(ok[1], full[1])
+    behind = d["means3D"].clone()
+    behind[::7, 2] -= 100.0
+    with pytest.raises(N.SfgsError, match="prefiltered"):
+        fwd(behind, prefiltered=True)
+    assert fwd(behind)[0] > 0                                   # without the promise the same input simply culls them
+    # empty band
+    rows = (cam.height + 15) // 16
+    empty = fwd(d["means3D"], tile_rows=(2, 2))
+    assert empty[0] == 0 and torch.equal(empty[5], full[5])     # nothing binned; radii still report full-image visibility
+    whole = fwd(d["means3D"], tile_rows=(0, rows + 5))          # end beyond the grid is clamped
+    assert whole[0] == full[0] and torch.equal(whole[1], full[1])

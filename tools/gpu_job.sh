@@ -10,8 +10,8 @@ for step in "$@"; do
     bench)     timeout 600 python bench.py > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err; echo "bench rc=$?"; cat gpurun_out/${tag}_bench.json | head -c 3000 ;;
     benchref)  timeout 600 python bench.py --impl reference > gpurun_out/${tag}_benchref.json 2> gpurun_out/${tag}_benchref.err; echo "benchref rc=$?"; cat gpurun_out/${tag}_benchref.json | head -c 1500 ;;
     host)      timeout 300 python tools/host_overhead.py > gpurun_out/${tag}_host.log 2>&1; echo "host rc=$?"; head -40 gpurun_out/${tag}_host.log ;;
-    launches)  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${tag}_launches.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/${tag}_launches.log 2>&1; echo "launches rc=$?" ;;
-    ncufull)   timeout 900 ncu --set full --clock-control none --import-source on -k regex:"render_|preprocess|tile_sort|gauss_bwd|scatter|tile_scan" -c 12 -o gpurun_out/${tag}_full -f python tests/gpu_profile_case.py > gpurun_out/${tag}_ncufull.log 2>&1; echo "ncufull rc=$?" ;;
+    launches)  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${tag}_launches.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-extras > gpurun_out/${tag}_launches.log 2>&1; echo "launches rc=$?" ;;
+    ncufull)   timeout 900 ncu --set full --clock-control none --import-source on -k regex:"render_|preprocess|tile_sort|gauss_bwd|scatter|tile_scan|acc_clear|ssim_|appearance_|filter3d" -s 14 -c 14 -o gpurun_out/${tag}_full -f python tests/gpu_profile_case.py --iters 2 --siblings > gpurun_out/${tag}_ncufull.log 2>&1; echo "ncufull rc=$?" ;;
     *)         echo "unknown step $step" ;;
   esac
 done
