@@ -626,7 +626,93 @@ def next_ops_record(dev):
     d = float((F3.compute_3D_filter(xyz_city, cams) - torch_filter()).abs().max())
     out["compute_3D_filter"] = {"P": P, "cameras": len(cams), "fused_ms": round(t_f, 4), "torch_eager_ms": round(t_t, 3),
                                 "speedup": round(t_t / t_f, 1), "max_abs_diff": d}
+    out.update(density_control_record(dev, timeit))
     return out
+
+
+def density_control_record(dev, timeit):
+    """Per-iteration densification statistics and densify_and_prune (train.py:311-322, scene/gaussian_model.py:564-749):
+    this library's kernels next to the reference's torch statements on the same tensors."""
+    from sfgs import densify as D
+    P = P_GAUSS
+    g = torch.Generator(device=dev).manual_seed(9)
+    r = lambda *s: torch.randn(*s, generator=g, device=dev)   # noqa: E731
+    par = {"xyz": r(P, 3) * 50, "f_dc": r(P, 1, 3), "f_rest": r(P, 15, 3) * 0.1, "opacity": r(P, 1) * 3,
+           "scaling": torch.log(torch.exp(r(P, 3) * 1.2) * 0.5), "rotation": r(P, 4)}
+    m = {k: r(*v.shape) * 1e-3 for k, v in par.items()}
+    v = {k: (r(*t.shape) * 1e-3) ** 2 for k, t in par.items()}
+    denom = torch.randint(0, 4, (P, 1), generator=g, device=dev).float()
+    accum = torch.rand((P, 1), generator=g, device=dev) * 3e-4 * denom
+    accum_abs = torch.rand((P, 1), generator=g, device=dev) * 6e-4 * denom
+    radii = torch.randint(-2, 30, (P,), generator=g, device=dev, dtype=torch.int32).clamp_min(0)
+    grad4 = r(P, 4) * 2e-4
+    stats = [torch.zeros(P, device=dev)] + [torch.zeros((P, 1), device=dev) for _ in range(4)]
+
+    def torch_stats():            # train.py:314 + gaussian_model.py:744-749
+        mr, a, aa, am, dn = stats
+        vis = radii > 0
+        mr[vis] = torch.max(mr[vis], radii[vis])
+        a[vis] += torch.norm(grad4[vis, :2], dim=-1, keepdim=True)
+        aa[vis] += torch.norm(grad4[vis, 2:], dim=-1, keepdim=True)
+        am[vis] = torch.max(am[vis], torch.norm(grad4[vis, 2:], dim=-1, keepdim=True))
+        dn[vis] += 1
+    t_stats = timeit(lambda: D.densification_stats(grad4, radii, *stats), n=20)
+    t_stats_torch = timeit(torch_stats, n=10)
+    extent, max_grad, pd = 120.0, 0.0002, 0.01
+    kw = dict(max_grad=max_grad, min_opacity=0.005, extent=extent, max_screen_size=20, percent_dense=pd)
+    Q = D.gradient_thresholds(accum, accum_abs, denom, max_grad)
+    _, _, _, t0 = D.densify_tensors(par, m, v, accum, accum_abs, denom, abs_threshold=Q, **kw)
+    noise = torch.randn((2 * t0["S"], 3), generator=g, device=dev)
+
+    def torch_densify():          # gaussian_model.py:653-735 with the optimizer surgery of :564-651, on the same tensors
+        st = {k: [par[k], m[k], v[k]] for k in par}
+
+        def append(new):
+            for k in st:
+                st[k] = [torch.cat((st[k][0], new[k])), torch.cat((st[k][1], torch.zeros_like(new[k]))),
+                         torch.cat((st[k][2], torch.zeros_like(new[k])))]
+
+        def prune(mask):
+            keep = ~mask
+            for k in st:
+                st[k] = [t[keep] for t in st[k]]
+        grads = accum / denom; grads[grads.isnan()] = 0.0
+        gabs = accum_abs / denom; gabs[gabs.isnan()] = 0.0
+        if not torch.isinf(gabs).any() and not torch.isnan(gabs).any():
+            q = torch.quantile(gabs.reshape(-1), 1 - (torch.norm(grads, dim=-1) >= max_grad).float().mean())
+        sel = (torch.norm(grads, dim=-1) >= max_grad) | (torch.norm(gabs, dim=-1) >= q)
+        sel = sel & (torch.exp(st["scaling"][0]).max(dim=1).values <= pd * extent)
+        append({k: st[k][0][sel] for k in st})
+        n = st["xyz"][0].shape[0]
+        pg = torch.zeros(n, device=dev); pg[:P] = grads.squeeze()
+        pa = torch.zeros(n, device=dev); pa[:P] = gabs.squeeze()
+        sel = ((pg >= max_grad) | (pa >= q)) & (torch.exp(st["scaling"][0]).max(dim=1).values > pd * extent)
+        stds = torch.exp(st["scaling"][0])[sel].repeat(2, 1)
+        samples = noise * stds
+        q4 = st["rotation"][0][sel]
+        q4 = q4 / q4.norm(dim=1, keepdim=True)
+        w, x, y, z = q4.unbind(1)
+        R = torch.stack([1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y), 2 * (x * y + w * z), 1 - 2 * (x * x + z * z),
+                         2 * (y * z - w * x), 2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)], dim=1).reshape(-1, 3, 3).repeat(2, 1, 1)
+        new = {k: st[k][0][sel].repeat(2, *([1] * (st[k][0].dim() - 1))) for k in st}
+        new["xyz"] = torch.bmm(R, samples.unsqueeze(-1)).squeeze(-1) + st["xyz"][0][sel].repeat(2, 1)
+        new["scaling"] = torch.log(stds / 1.6)
+        ns = int(sel.sum())
+        append(new)
+        prune(torch.cat((sel, torch.zeros(2 * ns, device=dev, dtype=torch.bool))))
+        pm = (torch.sigmoid(st["opacity"][0]) < 0.005).squeeze(-1) | (torch.exp(st["scaling"][0]).max(dim=1).values > 0.1 * extent)
+        prune(pm)
+        return st["xyz"][0].shape[0]
+    t_dens = timeit(lambda: D.densify_tensors(par, m, v, accum, accum_abs, denom, noise=noise, **kw), n=5)
+    t_dens_torch = timeit(torch_densify, n=3)
+    _, _, _, t = D.densify_tensors(par, m, v, accum, accum_abs, denom, noise=noise, **kw)
+    return {"densification_stats": {"P": P, "fused_ms": round(t_stats, 4), "torch_eager_ms": round(t_stats_torch, 3),
+                                    "speedup": round(t_stats_torch / t_stats, 1), "algorithmic_bytes": 52 * P,
+                                    "GBps": round(52 * P / t_stats / 1e6, 1), "note": "runs every training iteration below densify_until_iter"},
+            "densify_and_prune": {"P": P, "new_P": t["new_P"], "cloned": t["C"], "split": t["S"], "fused_ms": round(t_dens, 3),
+                                  "torch_eager_ms": round(t_dens_torch, 2), "speedup": round(t_dens_torch / t_dens, 1),
+                                  "same_point_count_as_torch": bool(torch_densify() == t["new_P"]),
+                                  "note": "both include the quantile (torch.quantile) and one host synchronisation; Adam moments moved with the rows"}}
 
 
 def live_traffic(kernel_regex, timeout_s=240):

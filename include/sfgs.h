@@ -41,7 +41,7 @@
 extern "C" {
 #endif
 
-#define SFGS_VERSION 3          /* 3: appearance_forward, overflow_reruns, selftest_expf; 2: out_norm_raw / norm_raw, two-phase backward, activations */
+#define SFGS_VERSION 4          /* 4: compute_3d_filter, densification_stats, densify_plan/apply; 3: appearance_forward, overflow_reruns, selftest_expf; 2: out_norm_raw / norm_raw, two-phase backward, activations */
 #define SFGS_TILE 16          /* BLOCK_X = BLOCK_Y = 16, RAST/cuda_rasterizer/config.h:15-17 */
 #define SFGS_MAX_EXTRA 34     /* MAX_EXTRA_DIMS, RAST/cuda_rasterizer/auxiliary.h:20 */
 
@@ -262,6 +262,37 @@ int sfgs_appearance_forward(int P, int D, int M, const float* features, const fl
  * filter_3D: [P] doubles out; scratch8: 8 bytes of device scratch. */
 int sfgs_compute_3d_filter(int P, const float* xyz, int C, const double* cams, double focal_max, double* filter_3D,
                            void* scratch8, void* stream);
+
+/* ---- adaptive density control -------------------------- */
+/* train.py:314-315 + GaussianModel.add_densification_stats (scene/gaussian_model.py:744-749) as one in-place pass:
+ * for every Gaussian with radii > 0: max_radii2D = max(max_radii2D, radii); grad_accum += |grad[:2]|;
+ * grad_accum_abs += |grad[2:]|; grad_accum_abs_max = max(., |grad[2:]|); denom += 1.
+ * viewspace_grad: [P,4] floats (16-byte aligned), the .grad of render()'s viewspace_points. */
+int sfgs_densification_stats(int P, const float* viewspace_grad, const int* radii, float* max_radii2D,
+                             float* grad_accum, float* grad_accum_abs, float* grad_accum_abs_max, float* denom,
+                             void* stream);
+/* GaussianModel.densify_and_prune (scene/gaussian_model.py:564-742) in two calls.
+ * plan: decides every Gaussian's fate from its own values (clone / split / prune rules of :653-735) and returns
+ *   totals_host = {surviving originals K, surviving clones KC, split sources S, surviving split sources KS, clone
+ *   selections C}; the new point count is K + KC + 2 KS.  abs_threshold: DEVICE scalar (the quantile of :708);
+ *   split_scale = percent_dense * extent; world_scale = 0.1 * extent; screen_test = (max_screen_size is truthy).
+ *   action: [P] bytes out; block_offsets: 5 * sfgs_densify_plan_blocks(P) ints out; totals_dev: 5 ints of device
+ *   scratch.  Synchronises the stream once (the caller must size the new tensors).
+ * apply: moves every surviving row of every field to its final place — originals with their Adam moments, clones and
+ *   split children with zero moments; a child's position is xyz + R(rotation) (noise * exp(scaling)), its scale
+ *   log(exp(scaling) / 1.6).  noise: [2 S, 3] standard-normal floats (child n of source s uses row n S + s, the
+ *   reference's .repeat(N, 1) order).  Fields: 0 xyz(3) 1 f_dc 2 f_rest 3 opacity(1) 4 scaling(3) 5 rotation(4), then
+ *   up to two more per-Gaussian parameters; src/dst[_exp_avg[_sq]] are host arrays of n_fields device pointers (the
+ *   three moment arrays may all be NULL when the optimizer has no state yet). */
+int sfgs_densify_plan_blocks(int P);
+int sfgs_densify_plan(int P, const float* grad_accum, const float* grad_accum_abs, const float* denom,
+                      const float* scaling, const float* opacity, float max_grad, const float* abs_threshold,
+                      float split_scale, float min_opacity, int screen_test, float max_screen_size, float world_scale,
+                      unsigned char* action, int* block_offsets, int* totals_dev, int totals_host[5], void* stream);
+int sfgs_densify_apply(int P, const unsigned char* action, const int* block_offsets, const int totals[5],
+                       const float* noise, int n_fields, const int* widths, const float* const* src,
+                       const float* const* src_exp_avg, const float* const* src_exp_avg_sq, float* const* dst,
+                       float* const* dst_exp_avg, float* const* dst_exp_avg_sq, void* stream);
 
 /* ---- fused SSIM ---------------------------------------------------------- */
 int sfgs_fusedssim_forward(float C1, float C2, int B, int CH, int H, int W,

@@ -20,7 +20,9 @@
 // core; SBO = 128 B between 8-row groups, LBO = bytes between the two 16-byte K chunks of one MMA); activations never
 // leave the SM: thread m packs row m of the A operand into the same layout, one elected thread issues the MMAs, the
 // fp32 accumulator lives in TMEM (128 lanes x 128 columns) and comes back with tcgen05.ld (lane m -> thread m) for the
-// bias + ReLU + bf16 pack of the next layer.  CTAs are persistent over tiles.
+// bias + ReLU + bf16 pack of the next layer.  CTAs are persistent over tiles and run TWO tiles at a time: two groups
+// of 128 threads, each with its own operand buffer, accumulator columns and mbarrier, synchronised only inside the
+// group (named barriers), so one group's epilogue arithmetic overlaps the other group's MMAs and loads.
 //
 // Precision: the multiplier head of a trained model is O(1) (h ~ 100 before the x0.01), so plain bf16 operands
 // (2^-9 relative) would leave ~1e-2 in the colours (measured on the golden vectors: 8e-3).  Every operand is therefore
@@ -34,21 +36,22 @@
 
 namespace {
 
-constexpr int AP_THREADS = 128;
+constexpr int AP_THREADS = 256;       // two groups of 128 threads, each with its own tile in flight
+constexpr int AP_GROUPS = 2;
 constexpr int AP_M = 128;            // Gaussians per tile
 constexpr int AP_H = 128;            // hidden width
 constexpr int AP_K1 = 32;            // 3 + 24 padded
 constexpr int AP_N3 = 16;            // 6 outputs padded to the smallest N of an M = 128 MMA
 constexpr int AP_G = 24, AP_E = 32;  // Fourier features per Gaussian, per-camera embedding size
-constexpr int AP_TMEM_COLS = 128;
+constexpr int AP_TMEM_COLS = 256;      // 128 accumulator columns per group
 
 struct alignas(128) ApSmem {                       // [2] = {hi, lo} halves of the split operands
-  __nv_bfloat16 A[2][AP_H / 8][AP_M / 8][8][8];     // 64 KB  activations, K-major cores: [k chunk][row group][row][8 k]
+  __nv_bfloat16 A[AP_GROUPS][2][AP_H / 8][AP_M / 8][8][8];   // 2 x 64 KB  activations, K-major cores: [k chunk][row group][row][8 k]
   __nv_bfloat16 W1[2][AP_K1 / 8][AP_H / 8][8][8];   // 16 KB  [k chunk][n group][n][8 k]
   __nv_bfloat16 W2[2][AP_H / 8][AP_H / 8][8][8];    // 64 KB
   __nv_bfloat16 W3[2][AP_H / 8][AP_N3 / 8][8][8];   //  8 KB
   float b1[AP_H], b2[AP_H], b3[8];
-  unsigned long long bar;
+  unsigned long long bar[AP_GROUPS];
   uint32_t tmem_base;
 };
 
@@ -76,9 +79,11 @@ __device__ __forceinline__ void umma_commit(unsigned long long* bar) {
 __device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
   const uint32_t a = (uint32_t)__cvta_generic_to_shared(bar);
   uint32_t ok;
+  uint32_t spins = 0;
   do {
     asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
                  : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+    if (!ok && ++spins > (1u << 24)) __trap();      // a lost completion becomes a launch failure, never a hung GPU
   } while (!ok);
 }
 // 32 consecutive fp32 columns of this thread's TMEM lane
@@ -133,8 +138,10 @@ appearance_fwd_kernel(int P, int D, const float* __restrict__ features /*[P,16,3
                       const float* __restrict__ means3D, const float* __restrict__ campos, float* __restrict__ colors) {
   extern __shared__ __align__(128) unsigned char ap_smem[];
   ApSmem& S = *reinterpret_cast<ApSmem*>(ap_smem);
-  const int t = threadIdx.x, warp = t >> 5;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int grp = tid >> 7, t = tid & 127;       // group and row inside the group's tile
   constexpr int IN = 3 + AP_G + AP_E;     // 59 columns of W1
+  auto group_sync = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory"); };
 
   // ---- once per CTA: TMEM, barrier, weights -> bf16 core-matrix layout, folded bias
   if (warp == 0) {
@@ -142,40 +149,60 @@ appearance_fwd_kernel(int P, int D, const float* __restrict__ features /*[P,16,3
                  ::"r"((uint32_t)__cvta_generic_to_shared(&S.tmem_base)), "r"(AP_TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  if (t == 0) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(&S.bar)) : "memory");
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(&S.bar[0])) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(&S.bar[1])) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  for (int i = t; i < AP_H * AP_K1; i += AP_THREADS) {          // W1[n][k], k < 27 (colour 3 + Fourier 24), zero padded
+  for (int i = tid; i < AP_H * AP_K1; i += AP_THREADS) {          // W1[n][k], k < 27 (colour 3 + Fourier 24), zero padded
     const int n = i / AP_K1, k = i - n * AP_K1;
     split_store(&S.W1[0][k >> 3][n >> 3][n & 7][k & 7], &S.W1[1][k >> 3][n >> 3][n & 7][k & 7], k < 3 + AP_G ? W1[n * IN + k] : 0.f);
   }
-  for (int i = t; i < AP_H * AP_H; i += AP_THREADS) {
+  for (int i = tid; i < AP_H * AP_H; i += AP_THREADS) {
     const int n = i / AP_H, k = i - n * AP_H;
     split_store(&S.W2[0][k >> 3][n >> 3][n & 7][k & 7], &S.W2[1][k >> 3][n >> 3][n & 7][k & 7], W2[i]);
   }
-  for (int i = t; i < AP_N3 * AP_H; i += AP_THREADS) {
+  for (int i = tid; i < AP_N3 * AP_H; i += AP_THREADS) {
     const int n = i / AP_H, k = i - n * AP_H;
     split_store(&S.W3[0][k >> 3][n >> 3][n & 7][k & 7], &S.W3[1][k >> 3][n >> 3][n & 7][k & 7], n < 6 ? W3[n * AP_H + k] : 0.f);
   }
-  {
-    float acc = b1[t];                                           // AP_THREADS == AP_H
+  if (tid < AP_H) {
+    float acc = b1[tid];
 #pragma unroll 8
-    for (int e = 0; e < AP_E; e++) acc = fmaf(W1[t * IN + 3 + AP_G + e], aemb[e], acc);
-    S.b1[t] = acc;
-    S.b2[t] = b2[t];
-    if (t < 8) S.b3[t] = t < 6 ? b3[t] : 0.f;
+    for (int e = 0; e < AP_E; e++) acc = fmaf(W1[tid * IN + 3 + AP_G + e], aemb[e], acc);
+    S.b1[tid] = acc;
+    S.b2[tid] = b2[tid];
+    if (tid < 8) S.b3[tid] = tid < 6 ? b3[tid] : 0.f;
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const uint32_t tmem = S.tmem_base;
-  const uint32_t tmem_lane = tmem + ((uint32_t)(warp * 32) << 16);      // this warp's quarter of the 128 lanes
+  const uint32_t tmem_all = S.tmem_base;
+  const uint32_t tmem = tmem_all + (uint32_t)(grp * 128);                   // this group's 128 accumulator columns
+  const uint32_t tmem_lane = tmem + ((uint32_t)((warp & 3) * 32) << 16);    // a warp reaches the lane quarter warp % 4
+  auto& A = S.A[grp];
+  unsigned long long* bar = &S.bar[grp];
   uint32_t phase = 0;
   const float cx = campos[0], cy = campos[1], cz = campos[2];
 
   const int ntiles = (P + AP_M - 1) / AP_M;
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+  // One thread per group asks L2 for the NEXT tile's rows (three contiguous spans) while this tile is computed: the
+  // row-per-thread loads below then find their lines in L2 instead of paying the HBM latency in the critical path.
+  auto prefetch_tile = [&](int tl) {
+    if (tl >= ntiles) return;
+    const int r0 = tl * AP_M;
+    const unsigned rows = (unsigned)((P - r0) < AP_M ? (P - r0) : AP_M);
+    const float* pf = features + (size_t)r0 * 48;
+    const float* pg = gemb + (size_t)r0 * AP_G;
+    const float* pm = means3D + (size_t)r0 * 3;
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(pf), "r"(rows * 192u) : "memory");
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(pg), "r"(rows * (unsigned)(AP_G * 4)) : "memory");
+    const unsigned mb = (rows * 12u) & ~15u;
+    if (mb && (reinterpret_cast<uintptr_t>(pm) & 15) == 0)
+      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(pm), "r"(mb) : "memory");
+  };
+  for (int tile = blockIdx.x * AP_GROUPS + grp; tile < ntiles; tile += gridDim.x * AP_GROUPS) {
+    if (t == 0) prefetch_tile(tile + gridDim.x * AP_GROUPS);
     const int g = tile * AP_M + t;
     const bool valid = g < P;
     const int gi = valid ? g : P - 1;                                   // rows past P shadow the last Gaussian
@@ -196,27 +223,27 @@ appearance_fwd_kernel(int P, int D, const float* __restrict__ features /*[P,16,3
       for (int kc = 0; kc < AP_K1 / 8; kc++) {
         uint4 hi, lo;
         split8(in + 8 * kc, hi, lo);
-        *reinterpret_cast<uint4*>(&S.A[0][kc][t >> 3][t & 7][0]) = hi;
-        *reinterpret_cast<uint4*>(&S.A[1][kc][t >> 3][t & 7][0]) = lo;
+        *reinterpret_cast<uint4*>(&A[0][kc][t >> 3][t & 7][0]) = hi;
+        *reinterpret_cast<uint4*>(&A[1][kc][t >> 3][t & 7][0]) = lo;
       }
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the MMA's async proxy
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
+    group_sync();
     // ---- layer 1: [128 x 32] x [32 x 128]
     if (t == 0) {
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
       for (int ks = 0; ks < AP_K1 / 16; ks++) {
-        const uint64_t ah = smem_desc(&S.A[0][2 * ks][0][0][0], 2048, 128), al = smem_desc(&S.A[1][2 * ks][0][0][0], 2048, 128);
+        const uint64_t ah = smem_desc(&A[0][2 * ks][0][0][0], 2048, 128), al = smem_desc(&A[1][2 * ks][0][0][0], 2048, 128);
         const uint64_t wh = smem_desc(&S.W1[0][2 * ks][0][0][0], 2048, 128), wl = smem_desc(&S.W1[1][2 * ks][0][0][0], 2048, 128);
         umma_bf16(tmem, ah, wh, instr_desc(AP_M, AP_H), ks > 0);
         umma_bf16(tmem, ah, wl, instr_desc(AP_M, AP_H), 1);
         umma_bf16(tmem, al, wh, instr_desc(AP_M, AP_H), 1);
       }
-      umma_commit(&S.bar);
+      umma_commit(bar);
     }
-    mbar_wait(&S.bar, phase); phase ^= 1;
+    mbar_wait(bar, phase); phase ^= 1;
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     // ---- h1 = relu(acc + b1') -> A (K = 128)
 #pragma unroll
@@ -229,27 +256,27 @@ appearance_fwd_kernel(int P, int D, const float* __restrict__ features /*[P,16,3
       for (int q = 0; q < 4; q++) {
         uint4 hi, lo;
         split8(v + 8 * q, hi, lo);
-        *reinterpret_cast<uint4*>(&S.A[0][(c0 >> 3) + q][t >> 3][t & 7][0]) = hi;
-        *reinterpret_cast<uint4*>(&S.A[1][(c0 >> 3) + q][t >> 3][t & 7][0]) = lo;
+        *reinterpret_cast<uint4*>(&A[0][(c0 >> 3) + q][t >> 3][t & 7][0]) = hi;
+        *reinterpret_cast<uint4*>(&A[1][(c0 >> 3) + q][t >> 3][t & 7][0]) = lo;
       }
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
+    group_sync();
     // ---- layer 2: [128 x 128] x [128 x 128]
     if (t == 0) {
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
       for (int ks = 0; ks < AP_H / 16; ks++) {
-        const uint64_t ah = smem_desc(&S.A[0][2 * ks][0][0][0], 2048, 128), al = smem_desc(&S.A[1][2 * ks][0][0][0], 2048, 128);
+        const uint64_t ah = smem_desc(&A[0][2 * ks][0][0][0], 2048, 128), al = smem_desc(&A[1][2 * ks][0][0][0], 2048, 128);
         const uint64_t wh = smem_desc(&S.W2[0][2 * ks][0][0][0], 2048, 128), wl = smem_desc(&S.W2[1][2 * ks][0][0][0], 2048, 128);
         umma_bf16(tmem, ah, wh, instr_desc(AP_M, AP_H), ks > 0);
         umma_bf16(tmem, ah, wl, instr_desc(AP_M, AP_H), 1);
         umma_bf16(tmem, al, wh, instr_desc(AP_M, AP_H), 1);
       }
-      umma_commit(&S.bar);
+      umma_commit(bar);
     }
-    mbar_wait(&S.bar, phase); phase ^= 1;
+    mbar_wait(bar, phase); phase ^= 1;
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
     for (int c0 = 0; c0 < AP_H; c0 += 32) {
@@ -261,27 +288,27 @@ appearance_fwd_kernel(int P, int D, const float* __restrict__ features /*[P,16,3
       for (int q = 0; q < 4; q++) {
         uint4 hi, lo;
         split8(v + 8 * q, hi, lo);
-        *reinterpret_cast<uint4*>(&S.A[0][(c0 >> 3) + q][t >> 3][t & 7][0]) = hi;
-        *reinterpret_cast<uint4*>(&S.A[1][(c0 >> 3) + q][t >> 3][t & 7][0]) = lo;
+        *reinterpret_cast<uint4*>(&A[0][(c0 >> 3) + q][t >> 3][t & 7][0]) = hi;
+        *reinterpret_cast<uint4*>(&A[1][(c0 >> 3) + q][t >> 3][t & 7][0]) = lo;
       }
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
+    group_sync();
     // ---- layer 3: [128 x 128] x [128 x 16]
     if (t == 0) {
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
       for (int ks = 0; ks < AP_H / 16; ks++) {
-        const uint64_t ah = smem_desc(&S.A[0][2 * ks][0][0][0], 2048, 128), al = smem_desc(&S.A[1][2 * ks][0][0][0], 2048, 128);
+        const uint64_t ah = smem_desc(&A[0][2 * ks][0][0][0], 2048, 128), al = smem_desc(&A[1][2 * ks][0][0][0], 2048, 128);
         const uint64_t wh = smem_desc(&S.W3[0][2 * ks][0][0][0], 256, 128), wl = smem_desc(&S.W3[1][2 * ks][0][0][0], 256, 128);
         umma_bf16(tmem, ah, wh, instr_desc(AP_M, AP_N3), ks > 0);
         umma_bf16(tmem, ah, wl, instr_desc(AP_M, AP_N3), 1);
         umma_bf16(tmem, al, wh, instr_desc(AP_M, AP_N3), 1);
       }
-      umma_commit(&S.bar);
+      umma_commit(bar);
     }
-    mbar_wait(&S.bar, phase); phase ^= 1;
+    mbar_wait(bar, phase); phase ^= 1;
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     float h[8];
     tmem_ld8(tmem_lane, h);
@@ -324,13 +351,13 @@ appearance_fwd_kernel(int P, int D, const float* __restrict__ features /*[P,16,3
       colors[3 * (size_t)g + 1] = fmaxf(rgb[1] + 0.5f, 0.f);
       colors[3 * (size_t)g + 2] = fmaxf(rgb[2] + 0.5f, 0.f);
     }
-    __syncthreads();      // every lane has read its accumulator columns and A before the next tile rewrites them
+    group_sync();      // every lane has read its accumulator columns and A before the next tile rewrites them
   }
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 0)
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(AP_TMEM_COLS) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_all), "r"(AP_TMEM_COLS) : "memory");
 }
 
 }  // namespace
@@ -361,7 +388,8 @@ extern "C" int sfgs_appearance_forward(int P, int D, int M, const float* feature
   }
   const int nsm = (dev >= 0 && dev < 64 && sms[dev] > 0) ? sms[dev] : 148;
   const int ntiles = (P + AP_M - 1) / AP_M;
-  const int grid = ntiles < nsm ? ntiles : nsm;              // persistent: one CTA per SM (154 KB of operands in shared memory)
+  const int pairs = (ntiles + AP_GROUPS - 1) / AP_GROUPS;
+  const int grid = pairs < nsm ? pairs : nsm;                // persistent: one CTA (two tile groups) per SM
   SFGS_COUNT_LAUNCH();
   appearance_fwd_kernel<<<grid, AP_THREADS, sizeof(ApSmem), (cudaStream_t)stream>>>(P, D, features, gemb, aemb, W1, b1, W2, b2,
                                                                                   W3, b3, means3D, campos, colors);

@@ -83,7 +83,7 @@ class BinningView(C.Structure):
 
 
 # every symbol include/sfgs.h declares
-ABI_VERSION = 3   # SFGS_VERSION of include/sfgs.h these struct mirrors were written for
+ABI_VERSION = 4   # SFGS_VERSION of include/sfgs.h these struct mirrors were written for
 
 EXPORTS = [
     "sfgs_rasterize_forward", "sfgs_rasterize_backward", "sfgs_mark_visible",
@@ -93,6 +93,7 @@ EXPORTS = [
     "sfgs_activations_forward", "sfgs_activations_backward",
     "sfgs_last_error", "sfgs_version", "sfgs_launch_count", "sfgs_profile_enable", "sfgs_profile_read", "sfgs_sizeof", "sfgs_sm_clock_probe",
     "sfgs_selftest_expf", "sfgs_overflow_reruns", "sfgs_appearance_forward", "sfgs_compute_3d_filter",
+    "sfgs_densification_stats", "sfgs_densify_plan_blocks", "sfgs_densify_plan", "sfgs_densify_apply",
 ]
 STAGE_NAMES = ["fwd_zero", "preprocess", "tile_scan", "emit_keys", "tile_sort", "render_fwd", "bwd_zero", "render_bwd",
                "gauss_bwd"]
@@ -147,6 +148,15 @@ def lib() -> C.CDLL:
     L.sfgs_appearance_forward.restype = C.c_int
     L.sfgs_compute_3d_filter.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]
     L.sfgs_compute_3d_filter.restype = C.c_int
+    L.sfgs_densification_stats.argtypes = [C.c_int] + [C.c_void_p] * 8
+    L.sfgs_densification_stats.restype = C.c_int
+    L.sfgs_densify_plan_blocks.argtypes = [C.c_int]; L.sfgs_densify_plan_blocks.restype = C.c_int
+    L.sfgs_densify_plan.argtypes = ([C.c_int] + [C.c_void_p] * 5 + [C.c_float, C.c_void_p, C.c_float, C.c_float, C.c_int,
+                                    C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int), C.c_void_p])
+    L.sfgs_densify_plan.restype = C.c_int
+    L.sfgs_densify_apply.argtypes = ([C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_int), C.c_void_p, C.c_int, C.POINTER(C.c_int)]
+                                     + [C.POINTER(C.c_void_p)] * 6 + [C.c_void_p])
+    L.sfgs_densify_apply.restype = C.c_int
     L.sfgs_selftest_expf.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.sfgs_selftest_expf.restype = C.c_int
     L.sfgs_profile_enable.argtypes = [C.c_int]; L.sfgs_profile_enable.restype = C.c_int

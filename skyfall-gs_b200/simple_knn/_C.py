@@ -36,5 +36,6 @@ def distCUDA2(points: torch.Tensor) -> torch.Tensor:
     with torch.cuda.device(pts.device):
         _N.check(L.sfgs_dist2_knn3(P, pts.data_ptr(), out.data_ptr(), cb, None,
                                    torch.cuda.current_stream(pts.device).cuda_stream), "sfgs_dist2_knn3")
-        torch.cuda.current_stream(pts.device).synchronize()   # scratch in `held` must outlive the kernels
+    # `held` (the scratch) was allocated on the current stream and the kernels were queued on it: returning the blocks
+    # to torch's caching allocator here is stream-ordered, exactly as for any torch op — no host synchronisation.
     return out

@@ -36,7 +36,7 @@ def test_struct_sizes_match_c():
 def test_version_and_layout_sizes():
     from sfgs import native
     L = native.lib()
-    assert L.sfgs_version() == 3
+    assert L.sfgs_version() == 4
     g1, g2 = L.sfgs_geom_bytes(1000), L.sfgs_geom_bytes(2000)
     assert 1000 * (64 + 24 + 1 + 4) <= g1 < g2
     assert L.sfgs_image_bytes(1920, 1080) >= 1920 * 1080 * 4 + 8160 * 12   # n_contrib + ranges + tile histogram
