@@ -407,7 +407,7 @@ def frame_record(name, impl_kind, dev, steps):
     d = make_inputs(scene, cam, dev)
     flush = L2Flusher(dev)
     step = {"ours": lambda: step_ours(d, cam), "stock": lambda: step_ref_stock(d, cam), "shim": lambda: step_ref(d, cam)}[impl_kind]
-    ms = timed_steps(step, steps, 5, flush, dev)
+    ms, timing = measure(step, steps, 5, flush, dev, max_attempts=4)      # same disturbance rule as the headline
     med = float(np.median(ms))
     f, _ = step()
     torch.cuda.synchronize(dev)
@@ -416,7 +416,7 @@ def frame_record(name, impl_kind, dev, steps):
     else:
         R, radii = int(f[0]), f[5]
     rec = {"name": name, "P": P, "extent": round(extent, 2), "camera": camname, "value": round(cam.width * cam.height / med / 1e3, 2),
-           "unit": "Mpix/s", "ms_per_step": round(med, 4), "ms_min": round(min(ms), 4), "ms_all": [round(m, 3) for m in ms], "steps": steps,
+           "unit": "Mpix/s", "ms_per_step": round(med, 4), "ms_min": round(min(ms), 4), "ms_all": [round(m, 3) for m in ms], "timing": timing, "steps": steps,
            "V": int((radii > 0).sum().item()), "R": R}
     if impl_kind == "ours":
         per_stage = {}
