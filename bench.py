@@ -434,6 +434,30 @@ def frame_record(name, impl_kind, dev, steps):
     return rec
 
 
+def knn_record(impl_kind, dev):
+    """distCUDA2 over the 1M scene's positions (scene initialisation, scene/gaussian_model.py:25): this library's grid
+    search vs the reference's Morton-order kernel (KNN/simple_knn.cu:186-222, compiled from its own sources)."""
+    pts = torch.from_numpy(S.city_scene(P_GAUSS, seed=0).means3D).to(dev)
+    if impl_kind == "ours":
+        from simple_knn._C import distCUDA2 as fn
+    else:
+        from oracle import ref_cuda
+        if not ref_cuda.available():
+            return None
+        fn = ref_cuda.knn
+    for _ in range(2):
+        out = fn(pts)
+    torch.cuda.synchronize(dev)
+    ts = []
+    for _ in range(5):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); out = fn(pts); b.record()
+        torch.cuda.synchronize(dev)
+        ts.append(a.elapsed_time(b))
+    return {"P": P_GAUSS, "ms": round(float(np.median(ts)), 3), "mean_dist2": float(out.mean()),
+            "timing": "CUDA events around the call (the reference's includes its own cudaMalloc/cudaMemcpy), median of 5"}
+
+
 def ssim_record(impl_kind, dev, steps=20):
     """fused-ssim forward(train) and backward at the training shape [1,3,1080,1920]; bytes per SURVEY 8d:
     forward reads 2 and writes 4 planes (72*N bytes at 3 channels), backward reads 6 and writes 1 (84*N)."""
@@ -940,6 +964,10 @@ def main():
             out["ssim"] = ssim_record(kind, dev)
         except Exception as exc:  # noqa: BLE001
             out["ssim"] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+        try:
+            out["knn"] = knn_record(kind, dev)
+        except Exception as exc:  # noqa: BLE001
+            out["knn"] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
         try:
             out["train_loop"] = train_loop_record(kind, dev)
         except Exception as exc:  # noqa: BLE001
