@@ -855,7 +855,7 @@ def main():
 
     # ---- tile-row sharded mode, same invocation (every rank takes part; strong scaling; SURVEY 8e / BASELINE configs[3])
     tilerows = None
-    if world > 1 and kind == "ours" and not args.no_extras:
+    if kind == "ours" and not args.no_extras:        # at N = 1 the same loop runs unsharded: the strong-scaling baseline
         from sfgs import multigpu
         del d
         torch.cuda.empty_cache()

@@ -209,7 +209,20 @@ def run_tilerows(P, extent, rank, world, dev, steps, warmup):
     # tile by tile, and no collective follows it.  Falls back to the NCCL path when peer mapping is unavailable.
     collective, step = "nccl reduce_scatter of the [P,16] blend-adjoint sums", step_nccl
     gather = "image all_gather (NCCL)"
-    if os.environ.get("SFGS_PEER_REDUCE", "1") != "0":
+
+    def step_single():          # world == 1: the same frame, the same loop, no exchange — the strong-scaling baseline
+        f = fwd(None)
+        last["R"] = f[0]
+        return f, bwd_full(f)
+
+    def bwd_full(f):
+        return R.rasterize_gaussians_backward(d["bg"], d["means3D"], f[5], e, d["scales"], d["rotations"], e, 1.0, e, e,
+                                              d["view"], d["proj"], cam.tanfovx, cam.tanfovy, 0.1, cot[0], cot[1],
+                                              cot[2], cot[3], e, d["shs"], 3, d["campos"], f[7], f[0], f[8], f[9], f[4],
+                                              False)
+    if world == 1:
+        collective, gather, step = "none (one GPU)", "none (one GPU)", step_single
+    elif os.environ.get("SFGS_PEER_REDUCE", "1") != "0":
         try:
             import torch.distributed._symmetric_memory as symm
             acc_sym = symm.empty((per * 16,), dtype=torch.float32, device=dev)
@@ -262,24 +275,46 @@ def run_tilerows(P, extent, rank, world, dev, steps, warmup):
             if rank == 0:
                 print(f"[tilerows] symmetric memory unavailable ({type(exc).__name__}: {exc}); using NCCL", file=sys.stderr)
 
+    multi = world > 1
     for _ in range(warmup):
         step()
-    dist.barrier()
+    if multi:
+        dist.barrier()
     torch.cuda.synchronize(dev)
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    import time
     a.record()
+    t_host = time.perf_counter()
     for _ in range(steps):
         step()
+    t_host = (time.perf_counter() - t_host) * 1e3 / steps      # host time to ISSUE a step (incl. the forward's one wait)
     b.record()
-    dist.barrier()
+    if multi:
+        dist.barrier()
     torch.cuda.synchronize(dev)
     ms = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
-    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    if multi:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     total = float(ms.item())
     R_band = torch.tensor([float(last["R"])], dtype=torch.float64, device=dev)
     R_all = [torch.zeros_like(R_band) for _ in range(world)]
-    dist.all_gather(R_all, R_band)
-    return {"workload": f"one 1920x1080 frame of the {scene.P}-Gaussian scene (extent {extent:g}) sharded by tile rows",
+    if multi:
+        dist.all_gather(R_all, R_band)
+    else:
+        R_all = [R_band]
+    # this rank's kernel times per stage (untimed extra steps; the library's own CUDA events), to show what shrinks with N
+    per_stage = {}
+    for _ in range(3):
+        N.profile_enable(True)
+        step()
+        torch.cuda.synchronize(dev)
+        for k, v in N.profile_read().items():
+            per_stage.setdefault(k, []).append(v[0] / v[1] if v[1] else 0.0)
+    N.profile_enable(False)
+    stages = {k: round(sorted(v)[len(v) // 2], 4) for k, v in per_stage.items()}
+    if multi:
+        dist.barrier()
+    return {"stages_ms_rank0": stages, "kernel_ms_rank0": round(sum(stages.values()), 4), "host_issue_ms_rank0": round(t_host, 4),"workload": f"one 1920x1080 frame of the {scene.P}-Gaussian scene (extent {extent:g}) sharded by tile rows",
             "P": scene.P, "value": round(steps * H * W / (total / 1e3) / 1e6, 2), "ms_per_step": round(total / steps, 4),
             "steps": steps, "warmup": warmup,
             "parallelism": f"tilerows x{world}: {gather} + {collective}; each rank finishes the gradients of P/N Gaussians",
