@@ -27,8 +27,9 @@ void sfgs_launch_preprocess(const sfgs_forward_args* a, const GeomLayout& g, con
 void sfgs_launch_mark_visible(int P, const float* means3D, const float* viewmatrix, unsigned char* present,
                               cudaStream_t st);
 void sfgs_launch_tile_scan(const ImageLayout& im, unsigned long long capacity, cudaStream_t st);
-void sfgs_launch_scatter(const ImageLayout& im, const BinningLayout& b, unsigned long long capacity, cudaStream_t st);
-void sfgs_launch_tile_sort(const GeomLayout& g, const ImageLayout& im, const BinningLayout& b, cudaStream_t st);
+void sfgs_launch_scatter(const GeomLayout& g, const ImageLayout& im, const BinningLayout& b, int P,
+                         unsigned long long capacity, cudaStream_t st);
+void sfgs_launch_tile_sort(const GeomLayout& g, const ImageLayout& im, const BinningLayout& b, int P, cudaStream_t st);
 void sfgs_launch_render_fwd(const sfgs_forward_args* a, const GeomLayout& g, const ImageLayout& im,
                             const BinningLayout& b, cudaStream_t st);
 void sfgs_launch_render_bwd(const sfgs_backward_args* a, const GeomLayout& g, const ImageLayout& im,
@@ -293,11 +294,11 @@ int sfgs_rasterize_forward(const sfgs_forward_args* a) {
     CU(cudaEventRecord(t_hdr.ev, st));
     if (P > 0) {
       PROF_BEGIN(ST_EMIT);
-      sfgs_launch_scatter(im, b, (unsigned long long)capacity, st);
+      sfgs_launch_scatter(g, im, b, a->P, (unsigned long long)capacity, st);
       PROF_END();
       STAGE_CHECK("scatter_keys");
       PROF_BEGIN(ST_SORT);
-      sfgs_launch_tile_sort(g, im, b, st);
+      sfgs_launch_tile_sort(g, im, b, a->P, st);
       PROF_END();
       STAGE_CHECK("tile_sort");
     }

@@ -12,6 +12,7 @@
 // shared memory.  The resulting (tile, depth, id) order — and therefore
 // point_list and ranges — is identical to the reference's, bit for bit.
 #include "sfgs_common.cuh"
+#include <cstdlib>
 
 namespace {
 
@@ -96,24 +97,51 @@ tile_scan_kernel(int tiles, const uint32_t* __restrict__ tile_count, uint2* __re
 
 // ---- key scatter ---------------------------------------------------------------
 // One thread per unsorted instance {gaussian, depth bits, tile, slot-in-tile}: no atomics, perfectly balanced.
-constexpr int SCATTER_ITEMS = 4;   // independent loads in flight per thread (the kernel is latency-bound)
+//
+// The kernel is latency-bound (four independent instances in flight per thread, ~10 % of the issue slots used), so it
+// also computes the instance's REACH MASK (which of the tile's eight 8x4-pixel blocks the splat's alpha >= 1/255
+// ellipse can touch, sfgs_common.cuh) from the Gaussian's blend record — the instances of one Gaussian are neighbours
+// in the unsorted list, so the 24 record bytes come from L1/L2 — and, when every Gaussian id fits 24 bits (PACK), carries
+// it through the sort in the low byte of the key:
+//     key = depth_bits << 32 | id << 8 | mask
+// (depth, id) is unique inside a tile, so the order is the order of depth_bits << 32 | id.  The sort kernels then touch
+// no Gaussian data at all; round 1/2a gathered 56 MB of records inside the sort CTAs to form the masks there.
+// With P >= 2^24 the key stays depth_bits << 32 | id and the sort kernels compute the masks as before.
+// SCATTER_ITEMS: instances per thread (independent loads in flight).  With the mask the kernel needs ~36 live floats per
+// instance in flight: one instance per thread keeps it at 60 registers (four CTAs per SM).
+template <bool PACK, int SCATTER_ITEMS>
 __global__ void __launch_bounds__(256)
 scatter_keys_kernel(const uint4* __restrict__ tmp, const uint2* __restrict__ ranges, const uint32_t* __restrict__ hdr,
-                    uint64_t* __restrict__ keys) {
+                    const float* __restrict__ rec, int gx, uint64_t* __restrict__ keys) {
   if (hdr[HDR_OVERFLOW]) return;
   const uint32_t R = hdr[HDR_R];
   const uint32_t i0 = blockIdx.x * (256u * SCATTER_ITEMS) + threadIdx.x;
   uint4 t[SCATTER_ITEMS];
   uint32_t start[SCATTER_ITEMS];
+  float4 r0[SCATTER_ITEMS];
+  float2 r1[SCATTER_ITEMS];
 #pragma unroll
   for (int u = 0; u < SCATTER_ITEMS; u++)
     if (i0 + 256u * u < R) t[u] = tmp[i0 + 256u * u];
 #pragma unroll
   for (int u = 0; u < SCATTER_ITEMS; u++)
-    if (i0 + 256u * u < R) start[u] = ranges[t[u].z].x;
+    if (i0 + 256u * u < R) {
+      start[u] = ranges[t[u].z].x;
+      if (PACK) {
+        r0[u] = *reinterpret_cast<const float4*>(rec + (size_t)t[u].x * REC_FLOATS);
+        r1[u] = *reinterpret_cast<const float2*>(rec + (size_t)t[u].x * REC_FLOATS + 4);
+      }
+    }
 #pragma unroll
   for (int u = 0; u < SCATTER_ITEMS; u++)
-    if (i0 + 256u * u < R) keys[start[u] + t[u].w] = ((uint64_t)t[u].y << 32) | t[u].x;
+    if (i0 + 256u * u < R) {
+      uint32_t lo = t[u].x;
+      if (PACK) {
+        const int tile_px = (int)(t[u].z % (uint32_t)gx) * SFGS_TILE, tile_py = (int)(t[u].z / (uint32_t)gx) * SFGS_TILE;
+        lo = (t[u].x << 8) | reach_mask(r0[u].x, r0[u].y, r0[u].z, r0[u].w, r1[u].x, r1[u].y, tile_px, tile_py);
+      }
+      keys[start[u] + t[u].w] = ((uint64_t)t[u].y << 32) | lo;
+    }
 }
 
 // ---- per-tile sort -------------------------------------------------------------
@@ -121,6 +149,18 @@ scatter_keys_kernel(const uint4* __restrict__ tmp, const uint2* __restrict__ ran
 // the common short lists and a heavy one (256 threads x 16 keys, 4096-key window, global radix fallback beyond
 // that); a CTA whose tile belongs to the other class exits at once.  Lists inside the window are sorted by the
 // shared-memory merge sort below (it replaced a bitonic network: 0.146 -> 0.135 ms on the benchmark frame).
+
+// Shared-memory sort buffers hold key i at PADIDX(i): one pad word per 16 keys.  A thread owns VT consecutive keys, so
+// without the pad the 32 lanes of a warp hit the same bank pair on every access (stride VT * 8 bytes = 64 or 128 bytes:
+// 16- / 32-way conflicts); with it every blocked access pattern of VT = 4, 8, 16 is the 2-wavefront minimum of a
+// 64-bit access.
+__device__ __forceinline__ int PADIDX(int i) { return i + (i >> 4); }
+
+// 64-bit compare-exchange of two registers (ascending)
+__device__ __forceinline__ void cex(uint64_t& a, uint64_t& b) {
+  const uint64_t lo = min(a, b), hi = max(a, b);
+  a = lo; b = hi;
+}
 
 // ---- merge sort of one tile's keys in shared memory ------------------------------------------------
 // Thread t owns keys [t*VT, (t+1)*VT): it sorts them in registers (odd-even transposition network), then
@@ -132,56 +172,75 @@ scatter_keys_kernel(const uint4* __restrict__ tmp, const uint2* __restrict__ ran
 // Keys are unique ((depth, id) with one instance per Gaussian and tile), so no stability rule is needed.
 // Returns the buffer that holds the sorted keys.
 template <int THREADS, int VT>
-__device__ __forceinline__ uint64_t* merge_sort_smem(uint64_t* a, uint64_t* b, const uint64_t* __restrict__ bucket, int n) {
+__device__ __forceinline__ void merge_sort_smem(uint64_t* buf /* PADIDX(THREADS*VT) keys */, int* s_lo /* [THREADS + 1] */,
+                                                const uint64_t* __restrict__ bucket, int n) {
   const int t = threadIdx.x;
   const int nchunks = (n + VT - 1) / VT;
   const int n_pad = nchunks * VT;
+  uint64_t k[VT];
   if (t < nchunks) {
-    uint64_t k[VT];
 #pragma unroll
     for (int i = 0; i < VT; i++) { const int idx = t * VT + i; k[i] = idx < n ? bucket[idx] : ~0ull; }
 #pragma unroll
-    for (int r = 0; r < VT; r++) {
+    for (int kk = 2; kk <= VT; kk <<= 1) {
 #pragma unroll
-      for (int i = (r & 1); i + 1 < VT; i += 2) {
-        const uint64_t lo = min(k[i], k[i + 1]), hi = max(k[i], k[i + 1]);
-        k[i] = lo; k[i + 1] = hi;
+      for (int j = kk >> 1; j > 0; j >>= 1) {
+#pragma unroll
+        for (int i = 0; i < VT; i++) {
+          const int l = i ^ j;
+          if (l > i) {
+            const bool up = (i & kk) == 0;
+            const uint64_t lo = min(k[i], k[l]), hi = max(k[i], k[l]);
+            k[i] = up ? lo : hi; k[l] = up ? hi : lo;
+          }
+        }
       }
     }
 #pragma unroll
-    for (int i = 0; i < VT; i++) a[t * VT + i] = k[i];
+    for (int i = 0; i < VT; i++) buf[PADIDX(t * VT + i)] = k[i];
   }
   __syncthreads();
-  uint64_t* src = a;
-  uint64_t* dst = b;
   for (int L = VT; L < n_pad; L <<= 1) {
+    const int out0 = t * VT;
+    const int pair0 = out0 & ~(2 * L - 1);                 // 2L is a power of two
+    const int lenA = min(L, max(0, n_pad - pair0));
+    const int lenB = min(L, max(0, n_pad - pair0 - L));
+    const int A0 = pair0, B0 = pair0 + L;
+    const int diag = out0 - pair0;
+    int lo = 0;
     if (t < nchunks) {
-      const int out0 = t * VT;
-      const int pair0 = out0 & ~(2 * L - 1);                 // 2L is a power of two
-      const int lenA = min(L, n_pad - pair0);
-      const int lenB = min(L, max(0, n_pad - pair0 - L));
-      const uint64_t* A = src + pair0;
-      const uint64_t* B = src + pair0 + L;
-      const int diag = out0 - pair0;
-      int lo = max(0, diag - lenB), hi = min(diag, lenA);
+      lo = max(0, diag - lenB);
+      int hi = min(diag, lenA);
       while (lo < hi) {                                      // first a with A[a] > B[diag-1-a]
         const int mid = (lo + hi) >> 1;
-        if (A[mid] <= B[diag - 1 - mid]) lo = mid + 1; else hi = mid;
-      }
-      int ai = lo, bi = diag - lo;
-      uint64_t ka = ai < lenA ? A[ai] : ~0ull, kb = bi < lenB ? B[bi] : ~0ull;
-#pragma unroll
-      for (int i = 0; i < VT; i++) {
-        const bool takeA = (bi >= lenB) || (ai < lenA && ka <= kb);
-        dst[out0 + i] = takeA ? ka : kb;
-        if (takeA) { ai++; ka = ai < lenA ? A[ai] : ~0ull; }
-        else { bi++; kb = bi < lenB ? B[bi] : ~0ull; }
+        if (buf[PADIDX(A0 + mid)] <= buf[PADIDX(B0 + diag - 1 - mid)]) lo = mid + 1; else hi = mid;
       }
     }
+    s_lo[t] = lo;
     __syncthreads();
-    uint64_t* tmp = src; src = dst; dst = tmp;
+    if (t < nchunks) {
+      const bool pair_end = ((out0 + VT) & (2 * L - 1)) == 0 || t + 1 >= nchunks;
+      const int a_end = pair_end ? lenA : s_lo[t + 1];
+      const int ai = lo, bi = diag - lo;
+      const int ca = a_end - ai;
+#pragma unroll
+      for (int i = 0; i < VT; i++) k[i] = buf[PADIDX(i < ca ? A0 + ai + i : B0 + bi + (VT - 1 - i))];
+    }
+    __syncthreads();                                         // every thread has its inputs: the buffer may be overwritten
+    if (t < nchunks) {
+#pragma unroll
+      for (int j = VT >> 1; j > 0; j >>= 1) {
+#pragma unroll
+        for (int i = 0; i < VT; i++) {
+          const int l = i ^ j;
+          if (l > i) cex(k[i], k[l]);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < VT; i++) buf[PADIDX(out0 + i)] = k[i];
+    }
+    __syncthreads();
   }
-  return src;
 }
 
 // stable LSD radix sort of n 64-bit keys, 8 bits per pass, one CTA of 256 threads, global ping-pong
@@ -230,37 +289,171 @@ __device__ void radix_global(uint64_t* a, uint64_t* b, int n, uint32_t* scratch 
   __syncthreads();
 }
 
-template <int THREADS, int WINDOW, int MIN_N>
-__global__ void __launch_bounds__(THREADS)
-tile_sort_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ hdr, uint64_t* __restrict__ keys,
+// canonical form of a key for the binning buffer (what the reference's sorted key list holds in its low 32 + depth bits)
+__device__ __forceinline__ uint64_t key_unpack(uint64_t k) { return (k & 0xffffffff00000000ull) | ((k >> 8) & 0xffffffull); }
+
+// Output of one sorted tile list: Gaussian ids, reach masks, and the sorted keys in canonical form.
+// PADDED: `sorted` is a shared-memory sort buffer (PADIDX layout); otherwise plain memory.
+template <bool PACK, int STRIDE, bool PADDED>
+__device__ __forceinline__ void emit_sorted(const uint64_t* sorted, uint64_t* bucket, int n, int first, uint32_t base,
+                                            uint32_t* __restrict__ point_list, unsigned char* __restrict__ inst_mask,
+                                            const float* __restrict__ rec, int tile, int gx) {
+  const int tile_px = (tile % gx) * SFGS_TILE, tile_py = (tile / gx) * SFGS_TILE;
+  for (int i = first; i < n; i += STRIDE) {
+    const uint64_t k = sorted[PADDED ? PADIDX(i) : i];
+    if (PACK) {
+      bucket[i] = key_unpack(k);
+      point_list[base + i] = (uint32_t)(k >> 8) & 0xffffffu;
+      inst_mask[base + i] = (unsigned char)(k & 0xffu);
+    } else {
+      const uint32_t id = (uint32_t)k;
+      if (PADDED) bucket[i] = k;
+      point_list[base + i] = id;
+      const float4 r0 = *reinterpret_cast<const float4*>(rec + (size_t)id * REC_FLOATS);
+      const float2 r1 = *reinterpret_cast<const float2*>(rec + (size_t)id * REC_FLOATS + 4);
+      inst_mask[base + i] = (unsigned char)reach_mask(r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, tile_px, tile_py);
+    }
+  }
+}
+
+// ---- lists of up to 512 instances: one WARP per tile ------------------------------------------------------------------
+// Every tile of the benchmark frames (130..490 instances) is in this class.  A CTA-wide sort of such a list keeps one or
+// two of its warps busy and parks the others at the pass barriers (ncu, round 2a: 4.9 barrier-stall cycles per issued
+// instruction, 19 of 32 lanes active, 51 % of the issue slots).  Here a warp owns a tile: lane t sorts VT keys in
+// registers (bitonic network, VT = 4 / 8 / 16 by list length), then log2(n/VT) merge-path passes run over two private
+// shared-memory buffers with only __syncwarp between them; four independent tiles per CTA, nothing block-wide.
+constexpr int WS_MAX = 512;           // longest list of the warp class
+constexpr int WS_WARPS = 4;           // tiles per CTA
+
+// Merge passes WITHOUT a serial merge loop.  A sequential two-pointer merge out of shared memory is one dependent
+// load -> compare -> select chain per output key (ncu, first version of this kernel: 9.3 short-scoreboard stall cycles
+// per issued instruction, 28 % of the issue slots, ~63 k cycles per tile).  Here a lane
+//   1. finds its merge-path split (ai, bi) by binary search — the only serial chain left, log2(L) steps;
+//   2. learns from its right neighbour's split how many of its VT outputs come from run A (ca) and run B (VT - ca);
+//   3. loads exactly those keys with VT INDEPENDENT shared-memory loads — A's ascending, B's in DESCENDING order, so the
+//      VT registers hold a bitonic sequence;
+//   4. sorts them with the log2(VT)-stage bitonic merge network (compile-time register indices, VT/2 independent
+//      compare-exchanges per stage) and stores them over the same buffer (all lanes have loaded: __syncwarp).
+// One shared buffer instead of two (4 KB per warp: twice the resident warps) and ~2400 issued instructions per
+// 276-key list, most of them independent.
+template <int VT>
+__device__ __forceinline__ void warp_merge_sort(uint64_t* buf, const uint64_t* __restrict__ bucket, int n, int lane) {
+  const int nchunks = (n + VT - 1) / VT;       // <= 32
+  const int n_pad = nchunks * VT;
+  uint64_t k[VT];
+  if (lane < nchunks) {
+#pragma unroll
+    for (int i = 0; i < VT; i++) { const int idx = lane * VT + i; k[i] = idx < n ? bucket[idx] : ~0ull; }
+    // bitonic sorting network over the VT registers (all indices are compile-time constants after unrolling)
+#pragma unroll
+    for (int kk = 2; kk <= VT; kk <<= 1) {
+#pragma unroll
+      for (int j = kk >> 1; j > 0; j >>= 1) {
+#pragma unroll
+        for (int i = 0; i < VT; i++) {
+          const int l = i ^ j;
+          if (l > i) {
+            const bool up = (i & kk) == 0;
+            const uint64_t lo = min(k[i], k[l]), hi = max(k[i], k[l]);
+            k[i] = up ? lo : hi; k[l] = up ? hi : lo;
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < VT; i++) buf[PADIDX(lane * VT + i)] = k[i];
+  }
+  __syncwarp();
+  for (int L = VT; L < n_pad; L <<= 1) {
+    const int out0 = lane * VT;
+    const int pair0 = out0 & ~(2 * L - 1);
+    const int lenA = min(L, max(0, n_pad - pair0));
+    const int lenB = min(L, max(0, n_pad - pair0 - L));
+    const int A0 = pair0, B0 = pair0 + L;                    // first keys of the two runs (logical indices)
+    const int diag = out0 - pair0;
+    int lo = 0;
+    if (lane < nchunks) {
+      lo = max(0, diag - lenB);
+      int hi = min(diag, lenA);
+      while (lo < hi) {                                      // first a with A[a] > B[diag-1-a]
+        const int mid = (lo + hi) >> 1;
+        if (buf[PADIDX(A0 + mid)] <= buf[PADIDX(B0 + diag - 1 - mid)]) lo = mid + 1; else hi = mid;
+      }
+    }
+    // split of the NEXT diagonal (diag + VT): the right neighbour's, or the end of run A at the end of the pair
+    const int lo_next = __shfl_down_sync(0xffffffffu, lo, 1);
+    if (lane < nchunks) {
+      const bool pair_end = ((out0 + VT) & (2 * L - 1)) == 0 || lane + 1 >= nchunks;
+      const int a_end = pair_end ? lenA : lo_next;
+      const int ai = lo, bi = diag - lo;
+      const int ca = a_end - ai;                             // keys taken from run A; VT - ca from run B
+#pragma unroll
+      for (int i = 0; i < VT; i++) k[i] = buf[PADIDX(i < ca ? A0 + ai + i : B0 + bi + (VT - 1 - i))];
+    }
+    __syncwarp();                                            // every lane has its inputs: the buffer may be overwritten
+    if (lane < nchunks) {
+#pragma unroll
+      for (int j = VT >> 1; j > 0; j >>= 1) {
+#pragma unroll
+        for (int i = 0; i < VT; i++) {
+          const int l = i ^ j;
+          if (l > i) cex(k[i], k[l]);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < VT; i++) buf[PADIDX(out0 + i)] = k[i];
+    }
+    __syncwarp();
+  }
+}
+
+template <bool PACK>
+__global__ void __launch_bounds__(WS_WARPS * 32)
+tile_sort_warp_kernel(int tiles, const uint2* __restrict__ ranges, const uint32_t* __restrict__ hdr, uint64_t* __restrict__ keys,
+                      uint32_t* __restrict__ point_list, const float* __restrict__ rec, int gx,
+                      unsigned char* __restrict__ inst_mask) {
+  if (hdr[HDR_OVERFLOW]) return;
+  __shared__ __align__(16) uint64_t s_keys[WS_WARPS][WS_MAX + WS_MAX / 16];      // 17 KB
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int tile = blockIdx.x * WS_WARPS + wid;
+  if (tile >= tiles) return;
+  const uint2 rg = ranges[tile];
+  const int n = (int)(rg.y - rg.x);
+  if (n == 0 || n > WS_MAX) return;               // empty, or a tile of the CTA-wide classes
+  uint64_t* bucket = keys + rg.x;
+  uint64_t* buf = s_keys[wid];
+  if (n <= 32 * 4) warp_merge_sort<4>(buf, bucket, n, lane);
+  else if (n <= 32 * 8) warp_merge_sort<8>(buf, bucket, n, lane);
+  else warp_merge_sort<16>(buf, bucket, n, lane);
+  emit_sorted<PACK, 32, true>(buf, bucket, n, lane, rg.x, point_list, inst_mask, rec, tile, gx);
+}
+
+// ---- longer lists: one CTA per tile, a small persistent grid strides over the tiles ------------------------------------
+// (a grid of one CTA per tile costs ~8 us of CTA launches even when no tile of the class exists — ncu, round 2b — and
+// the benchmark frames have none; here the CTAs of a class return after one header read in that case)
+template <int THREADS, int WINDOW, int MIN_N, bool PACK>
+__global__ void __launch_bounds__(THREADS, THREADS == 256 ? 3 : 8)
+tile_sort_kernel(int tiles, const uint2* __restrict__ ranges, const uint32_t* __restrict__ hdr, uint64_t* __restrict__ keys,
                  uint64_t* __restrict__ keys_tmp, uint32_t* __restrict__ point_list,
                  const float* __restrict__ rec, int gx, unsigned char* __restrict__ inst_mask) {
-  if (hdr[HDR_OVERFLOW]) return;
-  const uint2 rg = ranges[blockIdx.x];
-  const int n = (int)(rg.y - rg.x);
-  if (n <= MIN_N || (MIN_N == 0 && n > WINDOW)) return;   // other variant's tile (or empty)
+  if (hdr[HDR_OVERFLOW] || hdr[HDR_MAXTILE] <= (uint32_t)MIN_N) return;   // no tile of this class in the frame
   extern __shared__ __align__(16) unsigned char sort_smem[];
-  uint64_t* s = reinterpret_cast<uint64_t*>(sort_smem);        // [WINDOW]
-  uint64_t* s2 = s + WINDOW;                                    // [WINDOW]
-  uint64_t* bucket = keys + rg.x;
-  if (n <= WINDOW) {
-    const uint64_t* sorted = merge_sort_smem<THREADS, WINDOW / THREADS>(s, s2, bucket, n);
-    for (int i = threadIdx.x; i < n; i += THREADS) {
-      const uint64_t k = sorted[i];
-      bucket[i] = k;
-      point_list[rg.x + i] = (uint32_t)k;
+  // [PADIDX(WINDOW)] keys + [THREADS + 1] splits; the oversized-tile radix path reuses the space as 2560 scratch words
+  uint64_t* s = reinterpret_cast<uint64_t*>(sort_smem);
+  int* s_lo = reinterpret_cast<int*>(s + WINDOW + WINDOW / 16);
+  for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {     // block-uniform
+    const uint2 rg = ranges[tile];
+    const int n = (int)(rg.y - rg.x);
+    if (n <= MIN_N || (THREADS != 256 && n > WINDOW)) continue;   // other class's tile (or empty)
+    uint64_t* bucket = keys + rg.x;
+    if (n <= WINDOW) {
+      merge_sort_smem<THREADS, WINDOW / THREADS>(s, s_lo, bucket, n);
+      emit_sorted<PACK, THREADS, true>(s, bucket, n, threadIdx.x, rg.x, point_list, inst_mask, rec, tile, gx);
+    } else if (THREADS == 256) {
+      radix_global(bucket, keys_tmp + rg.x, n, reinterpret_cast<uint32_t*>(s));
+      emit_sorted<PACK, THREADS, false>(bucket, bucket, n, threadIdx.x, rg.x, point_list, inst_mask, rec, tile, gx);
     }
-  } else if (THREADS == 256) {
-    radix_global(bucket, keys_tmp + rg.x, n, reinterpret_cast<uint32_t*>(s));
-    for (int i = threadIdx.x; i < n; i += THREADS) point_list[rg.x + i] = (uint32_t)bucket[i];
-  }
-  // reach mask of every sorted instance (shared by the forward and backward blend kernels)
-  const int tile_px = (blockIdx.x % gx) * SFGS_TILE, tile_py = (blockIdx.x / gx) * SFGS_TILE;
-  for (int i = threadIdx.x; i < n; i += THREADS) {
-    const uint32_t id = (uint32_t)bucket[i];
-    const float4 r0 = *reinterpret_cast<const float4*>(rec + (size_t)id * REC_FLOATS);
-    const float2 r1 = *reinterpret_cast<const float2*>(rec + (size_t)id * REC_FLOATS + 4);
-    inst_mask[rg.x + i] = (unsigned char)reach_mask(r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, tile_px, tile_py);
+    __syncthreads();     // the shared buffers are reused by the next tile
   }
 }
 
@@ -271,23 +464,48 @@ void sfgs_launch_tile_scan(const ImageLayout& im, unsigned long long capacity, c
   tile_scan_kernel<<<1, SCAN_THREADS, 0, st>>>(im.tiles, im.tile_count, im.ranges, im.hdr, capacity);
 }
 
-void sfgs_launch_scatter(const ImageLayout& im, const BinningLayout& b, unsigned long long capacity, cudaStream_t st) {
+// Gaussian ids below 2^24 ride in the key together with the reach mask (see scatter_keys_kernel)
+static inline bool sfgs_keys_packed(int P) { return P <= (1 << 24); }
+
+void sfgs_launch_scatter(const GeomLayout& g, const ImageLayout& im, const BinningLayout& b, int P,
+                         unsigned long long capacity, cudaStream_t st) {
   SFGS_COUNT_LAUNCH();
-  const unsigned blocks = (unsigned)((capacity + 256 * SCATTER_ITEMS - 1) / (256 * SCATTER_ITEMS));
-  if (blocks == 0) return;
-  scatter_keys_kernel<<<blocks, 256, 0, st>>>(b.tmp, im.ranges, im.hdr, b.keys);
+  if (capacity == 0) return;
+  // instances per thread of the mask-forming scatter (default 2; SFGS_SCATTER_ITEMS=1|2|4 for A/B measurements)
+  static const int items = [] { const char* e = getenv("SFGS_SCATTER_ITEMS"); return e ? atoi(e) : 2; }();
+  auto blocks_for = [&](int it) { return (unsigned)((capacity + 256ull * it - 1) / (256ull * it)); };
+  if (!sfgs_keys_packed(P)) scatter_keys_kernel<false, 4><<<blocks_for(4), 256, 0, st>>>(b.tmp, im.ranges, im.hdr, g.rec, im.tiles_x, b.keys);
+  else if (items == 4) scatter_keys_kernel<true, 4><<<blocks_for(4), 256, 0, st>>>(b.tmp, im.ranges, im.hdr, g.rec, im.tiles_x, b.keys);
+  else if (items == 2) scatter_keys_kernel<true, 2><<<blocks_for(2), 256, 0, st>>>(b.tmp, im.ranges, im.hdr, g.rec, im.tiles_x, b.keys);
+  else scatter_keys_kernel<true, 1><<<blocks_for(1), 256, 0, st>>>(b.tmp, im.ranges, im.hdr, g.rec, im.tiles_x, b.keys);
 }
 
-void sfgs_launch_tile_sort(const GeomLayout& g, const ImageLayout& im, const BinningLayout& b, cudaStream_t st) {
-  constexpr size_t smem_light = 2 * 1024 * sizeof(uint64_t), smem_heavy = 2 * 4096 * sizeof(uint64_t);
+template <bool PACK>
+static void launch_tile_sorts(const GeomLayout& g, const ImageLayout& im, const BinningLayout& b, cudaStream_t st) {
+  constexpr size_t smem_mid = (1024 + 1024 / 16) * sizeof(uint64_t) + (128 + 1) * sizeof(int),
+                   smem_heavy = (4096 + 4096 / 16) * sizeof(uint64_t) + (256 + 1) * sizeof(int);
   static SfgsPerDeviceOnce attr_once;   // function attributes are per device
   if (attr_once.first_use()) {
-    cudaFuncSetAttribute(tile_sort_kernel<256, 4096, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_heavy);
+    cudaFuncSetAttribute(tile_sort_kernel<256, 4096, 1024, PACK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_heavy);
   }
   SFGS_COUNT_LAUNCH();
-  tile_sort_kernel<128, 1024, 0><<<im.tiles, 128, smem_light, st>>>(im.ranges, im.hdr, b.keys, b.keys_tmp, b.point_list,
-                                                                     g.rec, im.tiles_x, b.inst_mask);
+  tile_sort_warp_kernel<PACK><<<(im.tiles + WS_WARPS - 1) / WS_WARPS, WS_WARPS * 32, 0, st>>>(
+      im.tiles, im.ranges, im.hdr, b.keys, b.point_list, g.rec, im.tiles_x, b.inst_mask);
+  // the CTA-wide classes: persistent grids (resident CTAs of each kernel on every SM), returning at once when the
+  // frame's longest list (header word written by the scan) is below the class
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  { int v = 0; if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0) sms = v; }
+  const int grid_mid = im.tiles < 8 * sms ? im.tiles : 8 * sms, grid_heavy = im.tiles < 3 * sms ? im.tiles : 3 * sms;
   SFGS_COUNT_LAUNCH();
-  tile_sort_kernel<256, 4096, 1024><<<im.tiles, 256, smem_heavy, st>>>(im.ranges, im.hdr, b.keys, b.keys_tmp,
-                                                                        b.point_list, g.rec, im.tiles_x, b.inst_mask);
+  tile_sort_kernel<128, 1024, WS_MAX, PACK><<<grid_mid, 128, smem_mid, st>>>(im.tiles, im.ranges, im.hdr, b.keys, b.keys_tmp,
+                                                                             b.point_list, g.rec, im.tiles_x, b.inst_mask);
+  SFGS_COUNT_LAUNCH();
+  tile_sort_kernel<256, 4096, 1024, PACK><<<grid_heavy, 256, smem_heavy, st>>>(im.tiles, im.ranges, im.hdr, b.keys, b.keys_tmp,
+                                                                               b.point_list, g.rec, im.tiles_x, b.inst_mask);
+}
+
+void sfgs_launch_tile_sort(const GeomLayout& g, const ImageLayout& im, const BinningLayout& b, int P, cudaStream_t st) {
+  if (sfgs_keys_packed(P)) launch_tile_sorts<true>(g, im, b, st);
+  else launch_tile_sorts<false>(g, im, b, st);
 }

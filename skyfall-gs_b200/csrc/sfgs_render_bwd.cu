@@ -24,6 +24,7 @@
 //     ~320 G vector reductions/s, tools/red_bench.cu, so the ~16 M issued per frame hide behind the math):
 //     ~200x fewer global atomics than the reference and no block-wide barrier besides the staging one.
 #include "sfgs_common.cuh"
+#include <cstdlib>
 
 namespace {
 
@@ -48,6 +49,14 @@ struct BwdSmem {
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
   const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(s), "l"(gmem));
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::); }
@@ -351,14 +360,15 @@ render_bwd_kernel(const uint2* __restrict__ ranges, const char* __restrict__ bin
 // the benchmark frame: the reach mask is conservative) occupies a slot with zeros.
 constexpr int W4_CH = 16;
 struct alignas(16) WarpSmem {
-  float4 rec[2][W4_CH][4];      // 2 KB   the chunk's blend records, double buffered
-  uint2 pid[2][W4_CH];          // {list position, Gaussian id} of each slot
+  float4 rec[2][W4_CH][4];      // 2 KB   the chunk's blend records, double buffered; the free word [1].w of a staged
+                                //        record carries its list position (bits of a uint32)
+  uint32_t gid[2][W4_CH];       // Gaussian id of each slot
   float2 wh[32][W4_CH + 1];     // 4.25 KB phase-1 -> phase-2 hand-over, [pixel][slot], padded
   float pix[32][PIXF];          // 1.5 KB  per-pixel cotangents and coordinates
   uint32_t list[64];            // ring of collected list positions
 };
 
-template <bool PEER>
+template <bool PEER, bool FLAT>
 __global__ void __launch_bounds__(BWD_THREADS, 3)
 render_bwd_warp_kernel(const uint2* __restrict__ ranges, const char* __restrict__ binning_base,
                        const uint32_t* __restrict__ hdr, int W, int H, int band0,
@@ -457,10 +467,19 @@ render_bwd_warp_kernel(const uint2* __restrict__ ranges, const char* __restrict_
       const int r = lane >> 1, hf = lane & 1;
       const uint32_t pos = S.list[(head + r) & 63];
       const uint32_t id = point_list[range.x + pos];
-      const float* src = rec + (size_t)id * REC_FLOATS + hf * 8;
-      cp_async16(&S.rec[buf][r][hf * 2], src);
-      cp_async16(&S.rec[buf][r][hf * 2 + 1], src + 4);
-      if (hf == 0) S.pid[buf][r] = make_uint2(pos, id);
+      const float* src = rec + (size_t)id * REC_FLOATS;
+      // the record's second quad is (con.z, opacity, depth, free): it is copied as 8 + 4 bytes and the free word takes
+      // the list position, so phase 1 finds every per-record value it needs at an immediate offset of one base
+      if (hf == 0) {
+        cp_async16(&S.rec[buf][r][0], src);
+        cp_async16(&S.rec[buf][r][2], src + 8);
+        S.gid[buf][r] = id;
+      } else {
+        cp_async16(&S.rec[buf][r][3], src + 12);
+        cp_async8(&S.rec[buf][r][1], src + 4);
+        cp_async4(&S.rec[buf][r][1].z, src + 6);
+        S.rec[buf][r][1].w = __uint_as_float(pos);
+      }
     }
     cp_async_commit();
     head = (head + n) & 63;
@@ -476,7 +495,7 @@ render_bwd_warp_kernel(const uint2* __restrict__ ranges, const char* __restrict_
     const int slot = have_rec ? ck : 0;          // idle lanes shadow slot 0 (always valid, n >= 1)
     const float4 ra = S.rec[buf][slot][0];      // mx, my, con.x, con.y
     const float4 rb = S.rec[buf][slot][1];      // con.z, opac, depth
-    const uint32_t gid = S.pid[buf][slot].y;
+    const uint32_t gid = S.gid[buf][slot];
     float s0 = 0, s1 = 0, s2 = 0, s3 = 0, s4 = 0, s5 = 0, s6 = 0;      // sum w * dL/dpix_c
     float sh = 0, shx = 0, shy = 0, shxx = 0, shxy = 0, shyy = 0, sab = 0;
     const int pbase = chalf * 16;
@@ -527,41 +546,79 @@ render_bwd_warp_kernel(const uint2* __restrict__ ranges, const char* __restrict_
     __syncwarp();                                   // chunk `buf` has landed and is visible to the whole warp
     const int n_next = scan_gather(buf ^ 1);        // the next chunk's gather overlaps the math below
     // ---- phase 1: pixel-parallel recursion over the chunk's records, slot order = back to front
-#pragma unroll
-    for (int k = 0; k < W4_CH; k++) {
-      if (k < n_cur) {                              // warp-uniform
-        const float4 ra = S.rec[buf][k][0];         // mx, my, con.x, con.y
-        const float4 rb = S.rec[buf][k][1];         // con.z, opac, depth
-        const uint32_t pos = S.pid[buf][k].x;
-        const float dx = ra.x - pixfx, dy = ra.y - pixfy;
-        const float power = -0.5f * (ra.z * dx * dx + rb.x * dy * dy) - ra.w * dx * dy;
-        const float G = sfgs_expf(power, ek);
-        const float alpha = min(0.99f, rb.y * G);
-        const bool active = (pos < last_contributor) && !(power > 0.0f) && !(alpha < 1.0f / 255.0f);
-        float w_out = 0.f, h_out = 0.f;
-        if (active) {
-          const float4 rc = S.rec[buf][k][2];       // r, g, b, nx
-          const float4 rd = S.rec[buf][k][3];       // ny, nz
-          // 1 - alpha is in [0.01, 1]: the approximate reciprocal (1 ulp, one MUFU) needs no range fix-up; it is shared
-          // by the T recovery and the background term
-          float inv_1ma;
-          asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv_1ma) : "f"(1.f - alpha));
-          T = T * inv_1ma;
-          // two independent chains: halves the dependent-FMA latency of the dot product
-          float g = rc.x * dLc0, g2 = rc.w * dLn0;
-          g += rc.y * dLc1; g2 += rd.x * dLn1;
-          g += rc.z * dLc2; g2 += rd.y * dLn2;
-          g += rb.z * dLd;  g2 += dLa;
-          g += g2;
-          A = last_alpha * g_last + (1.f - last_alpha) * A;
-          g_last = g;
-          last_alpha = alpha;
-          const float dL_dalpha = fmaf(tb, inv_1ma, T * (g - A));
-          w_out = alpha * T;
-          h_out = G * dL_dalpha;
-        }
-        S.wh[lane][k] = make_float2(w_out, h_out);
+    auto slot_body = [&](const int k, const float4 ra, const float4 rb) {
+      const float dx = ra.x - pixfx, dy = ra.y - pixfy;
+      const float power = -0.5f * (ra.z * dx * dx + rb.x * dy * dy) - ra.w * dx * dy;
+      const float G = sfgs_expf(power, ek);
+      const float alpha = min(0.99f, rb.y * G);
+      const bool active = (__float_as_uint(rb.w) < last_contributor) && !(power > 0.0f) && !(alpha < 1.0f / 255.0f);
+      float w_out = 0.f, h_out = 0.f;
+      if (FLAT) {
+        // branch-free form: a chunk is one basic block, so the scheduler can overlap slot k+1's load -> exp chain with
+        // slot k's recursion (a (block, record) pair that no pixel blends is 0.6 % of the pairs: the work a branch would
+        // skip is negligible, the selects cost what the branch bookkeeping did)
+        const float4 rc = S.rec[buf][k][2];       // r, g, b, nx
+        const float4 rd = S.rec[buf][k][3];       // ny, nz
+        float inv_1ma;
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv_1ma) : "f"(1.f - alpha));
+        const float Tn = T * inv_1ma;
+        float g = rc.x * dLc0, g2 = rc.w * dLn0;
+        g += rc.y * dLc1; g2 += rd.x * dLn1;
+        g += rc.z * dLc2; g2 += rd.y * dLn2;
+        g += rb.z * dLd;  g2 += dLa;
+        g += g2;
+        const float An = last_alpha * g_last + (1.f - last_alpha) * A;
+        const float dL_dalpha = fmaf(tb, inv_1ma, Tn * (g - An));
+        w_out = active ? alpha * Tn : 0.f;
+        h_out = active ? G * dL_dalpha : 0.f;
+        T = active ? Tn : T;
+        A = active ? An : A;
+        g_last = active ? g : g_last;
+        last_alpha = active ? alpha : last_alpha;
+      } else if (active) {
+        const float4 rc = S.rec[buf][k][2];       // r, g, b, nx
+        const float4 rd = S.rec[buf][k][3];       // ny, nz
+        // 1 - alpha is in [0.01, 1]: the approximate reciprocal (1 ulp, one MUFU) needs no range fix-up; it is shared
+        // by the T recovery and the background term
+        float inv_1ma;
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv_1ma) : "f"(1.f - alpha));
+        T = T * inv_1ma;
+        // two independent chains: halves the dependent-FMA latency of the dot product
+        float g = rc.x * dLc0, g2 = rc.w * dLn0;
+        g += rc.y * dLc1; g2 += rd.x * dLn1;
+        g += rc.z * dLc2; g2 += rd.y * dLn2;
+        g += rb.z * dLd;  g2 += dLa;
+        g += g2;
+        A = last_alpha * g_last + (1.f - last_alpha) * A;
+        g_last = g;
+        last_alpha = alpha;
+        const float dL_dalpha = fmaf(tb, inv_1ma, T * (g - A));
+        w_out = alpha * T;
+        h_out = G * dL_dalpha;
       }
+      S.wh[lane][k] = make_float2(w_out, h_out);
+    };
+    auto slot = [&](const int k) {
+      slot_body(k, S.rec[buf][k][0] /* mx, my, con.x, con.y */, S.rec[buf][k][1] /* con.z, opac, depth, list position */);
+    };
+    if (n_cur == W4_CH) {                           // every chunk of a warp but its last: no per-slot bound test
+      if (FLAT) {
+        // slot k+1's parameters are read before slot k's hand-over store (the compiler cannot move a shared-memory
+        // load above that store on its own), so their latency overlaps slot k's arithmetic
+        float4 ra_n = S.rec[buf][0][0], rb_n = S.rec[buf][0][1];
+#pragma unroll
+        for (int k = 0; k < W4_CH; k++) {
+          const float4 ra = ra_n, rb = rb_n;
+          if (k + 1 < W4_CH) { ra_n = S.rec[buf][k + 1][0]; rb_n = S.rec[buf][k + 1][1]; }
+          slot_body(k, ra, rb);
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < W4_CH; k++) slot(k);
+      }
+    } else {
+#pragma unroll 1
+      for (int k = 0; k < n_cur; k++) slot(k);
     }
     phase2(n_cur, buf);
     buf ^= 1;
@@ -598,13 +655,19 @@ void sfgs_launch_render_bwd(const sfgs_backward_args* a, const GeomLayout& g, co
     const size_t wsmem = sizeof(WarpSmem) * BWD_WARPS;
     static SfgsPerDeviceOnce warp_once;
     if (warp_once.first_use()) {
-      cudaFuncSetAttribute(render_bwd_warp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem);
-      cudaFuncSetAttribute(render_bwd_warp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem);
+      cudaFuncSetAttribute(render_bwd_warp_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem);
+      cudaFuncSetAttribute(render_bwd_warp_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem);
+      cudaFuncSetAttribute(render_bwd_warp_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem);
+      cudaFuncSetAttribute(render_bwd_warp_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem);
     }
+    // the branch-free form is the default; SFGS_BWD_FLAT=0 selects the branching one (A/B measurements)  — branch-free phase 1
+    static const bool flat = [] { const char* e = getenv("SFGS_BWD_FLAT"); return !(e && e[0] == '0'); }();
 #define RBW_ARGS im.ranges, (const char*)b.point_list, im.hdr, a->width, a->height, band0, a->background, g.rec,       \
       a->accum_alphas, im.n_contrib, a->dL_dpix, a->dL_dpix_depth, a->dL_dpix_norm, a->dL_dpix_alpha, a->norm_raw, acc, pt
-    if (peer) render_bwd_warp_kernel<true><<<grid, BWD_THREADS, wsmem, st>>>(RBW_ARGS);
-    else render_bwd_warp_kernel<false><<<grid, BWD_THREADS, wsmem, st>>>(RBW_ARGS);
+    if (peer && flat) render_bwd_warp_kernel<true, true><<<grid, BWD_THREADS, wsmem, st>>>(RBW_ARGS);
+    else if (peer) render_bwd_warp_kernel<true, false><<<grid, BWD_THREADS, wsmem, st>>>(RBW_ARGS);
+    else if (flat) render_bwd_warp_kernel<false, true><<<grid, BWD_THREADS, wsmem, st>>>(RBW_ARGS);
+    else render_bwd_warp_kernel<false, false><<<grid, BWD_THREADS, wsmem, st>>>(RBW_ARGS);
 #undef RBW_ARGS
     return;
   }

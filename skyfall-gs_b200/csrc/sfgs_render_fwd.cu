@@ -15,6 +15,7 @@
 // alpha >= 1/255 ellipse can touch its block (bit lists built with ballots), which
 // removes ~80% of the (pixel, Gaussian) evaluations without changing any result.
 #include "sfgs_common.cuh"
+#include <cstdlib>
 
 namespace {
 
@@ -25,6 +26,14 @@ constexpr int FWD_STAGES = 2;
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
   const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(s), "l"(gmem));
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int N>
@@ -266,11 +275,12 @@ render_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
 // immediate offsets, and a warp whose 32 pixels are saturated stops scanning on its own.
 constexpr int F4_CH = 16;
 struct alignas(16) FwdWarpSmem {
-  float4 rec[2][F4_CH][4];      // 2 KB   the chunk's blend records, double buffered
-  uint32_t pos[2][F4_CH];       // 1-based list position of each slot
+  float4 rec[2][F4_CH][4];      // 2 KB   the chunk's blend records, double buffered; the free word [1].w of a staged
+                                //        record carries its 1-based list position (bits of a uint32)
   uint32_t list[64];            // ring of collected list positions
 };
 
+template <bool FLAT>
 __global__ void __launch_bounds__(FWD_THREADS)
 render_fwd_warp_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list,
                        const unsigned char* __restrict__ inst_mask, const uint32_t* __restrict__ hdr, int W, int H,
@@ -321,10 +331,18 @@ render_fwd_warp_kernel(const uint2* __restrict__ ranges, const uint32_t* __restr
       const int r = lane >> 1, hf = lane & 1;
       const uint32_t pos = S.list[(head + r) & 63];
       const uint32_t id = point_list[range.x + pos];
-      const float* src = rec + (size_t)id * REC_FLOATS + hf * 8;
-      cp_async16(&S.rec[buf][r][hf * 2], src);
-      cp_async16(&S.rec[buf][r][hf * 2 + 1], src + 4);
-      if (hf == 0) S.pos[buf][r] = pos + 1u;       // 1-based: the value n_contrib records
+      const float* src = rec + (size_t)id * REC_FLOATS;
+      // the record's second quad is (con.z, opacity, depth, free): copied as 8 + 4 bytes, the free word takes the
+      // 1-based list position (the value n_contrib records), so the blend loop reads it with the quad it loads anyway
+      if (hf == 0) {
+        cp_async16(&S.rec[buf][r][0], src);
+        cp_async16(&S.rec[buf][r][2], src + 8);
+      } else {
+        cp_async16(&S.rec[buf][r][3], src + 12);
+        cp_async8(&S.rec[buf][r][1], src + 4);
+        cp_async4(&S.rec[buf][r][1].z, src + 6);
+        S.rec[buf][r][1].w = __uint_as_float(pos + 1u);
+      }
     }
     cp_async_commit();
     head = (head + n) & 63;
@@ -339,31 +357,54 @@ render_fwd_warp_kernel(const uint2* __restrict__ ranges, const uint32_t* __restr
     __syncwarp();                                   // chunk `buf` has landed and is visible to the whole warp
     if (__all_sync(0xffffffffu, T == 0.0f)) break;  // every pixel of the block is saturated (or outside the image)
     const int n_next = scan_gather(buf ^ 1);        // the next chunk's gather overlaps the math below
-#pragma unroll
-    for (int k = 0; k < F4_CH; k++) {
-      if (k < n_cur) {                              // warp-uniform
-        const float4 a = S.rec[buf][k][0];          // mx, my, con.x, con.y
-        const float4 c = S.rec[buf][k][1];          // con.z, opac, depth, -
-        const float dx = a.x - pixfx, dy = a.y - pixfy;
-        const float power = -0.5f * (a.z * dx * dx + c.x * dy * dy) - a.w * dx * dy;
-        if (!(power > 0.0f)) {
-          const float alpha = min(0.99f, c.y * sfgs_expf(power, ek));
-          if (!(alpha < 1.0f / 255.0f)) {
-            const float test_T = T * (1 - alpha);
-            if (test_T < 0.0001f) { T_done = fmaxf(T_done, T); T = 0.0f; }
-            else {
-              const float4 f = S.rec[buf][k][2];    // r, g, b, nx
-              const float4 g = S.rec[buf][k][3];    // ny, nz
-              const float w = alpha * T;            // see render_fwd_kernel for the association of each output
-              C0 = fmaf(f.x, w, C0); C1 = fmaf(f.y, w, C1); C2 = fmaf(f.z, w, C2);
-              Dp += c.z * alpha * T;
-              N0 = fmaf(f.w, w, N0); N1 = fmaf(g.x, w, N1); N2 = fmaf(g.y, w, N2);
-              T = test_T;
-              last_contributor = S.pos[buf][k];
-            }
+    auto slot_body = [&](const int k, const float4 a, const float4 c) {
+      const float dx = a.x - pixfx, dy = a.y - pixfy;
+      const float power = -0.5f * (a.z * dx * dx + c.x * dy * dy) - a.w * dx * dy;
+      if (FLAT) {
+        // branch-free form (one basic block per chunk: slot k+1's load -> exp chain overlaps slot k's accumulation).
+        // A pair that is not applied multiplies every accumulator update by an exact 0.
+        const float4 f = S.rec[buf][k][2];      // r, g, b, nx
+        const float4 g = S.rec[buf][k][3];      // ny, nz
+        const float alpha = min(0.99f, c.y * sfgs_expf(power, ek));
+        const bool ok = !(power > 0.0f) && !(alpha < 1.0f / 255.0f);
+        const float test_T = T * (1 - alpha);
+        const bool stop = ok && (test_T < 0.0001f);
+        const bool apply = ok && !stop;
+        const float Ta = apply ? T : 0.0f;
+        const float w = alpha * Ta;
+        C0 = fmaf(f.x, w, C0); C1 = fmaf(f.y, w, C1); C2 = fmaf(f.z, w, C2);
+        Dp = fmaf(c.z * alpha, Ta, Dp);           // (depth * alpha) * T, the reference's association
+        N0 = fmaf(f.w, w, N0); N1 = fmaf(g.x, w, N1); N2 = fmaf(g.y, w, N2);
+        T_done = stop ? fmaxf(T_done, T) : T_done;
+        T = apply ? test_T : (stop ? 0.0f : T);
+        last_contributor = apply ? __float_as_uint(c.w) : last_contributor;
+      } else if (!(power > 0.0f)) {
+        const float alpha = min(0.99f, c.y * sfgs_expf(power, ek));
+        if (!(alpha < 1.0f / 255.0f)) {
+          const float test_T = T * (1 - alpha);
+          if (test_T < 0.0001f) { T_done = fmaxf(T_done, T); T = 0.0f; }
+          else {
+            const float4 f = S.rec[buf][k][2];    // r, g, b, nx
+            const float4 g = S.rec[buf][k][3];    // ny, nz
+            const float w = alpha * T;            // see render_fwd_kernel for the association of each output
+            C0 = fmaf(f.x, w, C0); C1 = fmaf(f.y, w, C1); C2 = fmaf(f.z, w, C2);
+            Dp += c.z * alpha * T;
+            N0 = fmaf(f.w, w, N0); N1 = fmaf(g.x, w, N1); N2 = fmaf(g.y, w, N2);
+            T = test_T;
+            last_contributor = __float_as_uint(c.w);
           }
         }
       }
+    };
+    auto slot = [&](const int k) {
+      slot_body(k, S.rec[buf][k][0] /* mx, my, con.x, con.y */, S.rec[buf][k][1] /* con.z, opac, depth, 1-based list position */);
+    };
+    if (n_cur == F4_CH) {                           // every chunk of a warp but its last: no per-slot bound test
+#pragma unroll
+      for (int k = 0; k < F4_CH; k++) slot(k);
+    } else {
+#pragma unroll 1
+      for (int k = 0; k < n_cur; k++) slot(k);
     }
     buf ^= 1;
     n_cur = n_next;
@@ -417,9 +458,13 @@ void sfgs_launch_render_fwd(const sfgs_forward_args* a, const GeomLayout& g, con
   SFGS_COUNT_LAUNCH();
 #if !SFGS_TMA_STAGING
   if (a->ED == 0) {   // default path: warp-private pipelines (render_fwd_warp_kernel)
-    render_fwd_warp_kernel<<<grid, FWD_THREADS, 0, st>>>(im.ranges, b.point_list, b.inst_mask, im.hdr, a->width, a->height, band0,
-                                                        g.rec, a->background, a->out_color, a->out_depth, a->out_norm,
-                                                        a->out_norm_raw, a->out_alpha, im.n_contrib, op);
+    // the branch-free form is the default; SFGS_FWD_FLAT=0 selects the branching one (A/B measurements)  — branch-free blend loop
+    static const bool flat = [] { const char* e = getenv("SFGS_FWD_FLAT"); return !(e && e[0] == '0'); }();
+#define RFW_ARGS im.ranges, b.point_list, b.inst_mask, im.hdr, a->width, a->height, band0, g.rec, a->background, a->out_color,   \
+      a->out_depth, a->out_norm, a->out_norm_raw, a->out_alpha, im.n_contrib, op
+    if (flat) render_fwd_warp_kernel<true><<<grid, FWD_THREADS, 0, st>>>(RFW_ARGS);
+    else render_fwd_warp_kernel<false><<<grid, FWD_THREADS, 0, st>>>(RFW_ARGS);
+#undef RFW_ARGS
     return;
   }
 #endif
