@@ -205,7 +205,7 @@ typedef struct sfgs_geom_view {
 typedef struct sfgs_image_view {
   const uint32_t* n_contrib;   /* [H*W] */
   const uint32_t* ranges;      /* [tiles,2] (start,end) into point_list */
-  const uint32_t* tile_count;  /* [tiles] */
+  const uint32_t* tile_count;  /* [tiles] scratch: the per-tile instance histogram, counted back to zero by the key scatter (all zero after a forward) */
 } sfgs_image_view;
 typedef struct sfgs_binning_view {
   const uint64_t* keys;        /* [R] (depth_bits<<32 | gaussian) grouped by tile, sorted inside each tile */

@@ -96,7 +96,7 @@ tile_scan_kernel(int tiles, const uint32_t* __restrict__ tile_count, uint2* __re
 }
 
 // ---- key scatter ---------------------------------------------------------------
-// One thread per unsorted instance {gaussian, depth bits, tile, slot-in-tile}: no atomics, perfectly balanced.
+// One thread per unsorted instance {gaussian, depth bits, tile}: perfectly balanced.
 //
 // The kernel is latency-bound (four independent instances in flight per thread, ~10 % of the issue slots used), so it
 // also computes the instance's REACH MASK (which of the tile's eight 8x4-pixel blocks the splat's alpha >= 1/255
@@ -111,13 +111,13 @@ tile_scan_kernel(int tiles, const uint32_t* __restrict__ tile_count, uint2* __re
 // instance in flight: one instance per thread keeps it at 60 registers (four CTAs per SM).
 template <bool PACK, int SCATTER_ITEMS>
 __global__ void __launch_bounds__(256)
-scatter_keys_kernel(const uint4* __restrict__ tmp, const uint2* __restrict__ ranges, const uint32_t* __restrict__ hdr,
-                    const float* __restrict__ rec, int gx, uint64_t* __restrict__ keys) {
+scatter_keys_kernel(const uint4* __restrict__ tmp, const uint2* __restrict__ ranges, uint32_t* __restrict__ tile_count,
+                    const uint32_t* __restrict__ hdr, const float* __restrict__ rec, int gx, uint64_t* __restrict__ keys) {
   if (hdr[HDR_OVERFLOW]) return;
   const uint32_t R = hdr[HDR_R];
   const uint32_t i0 = blockIdx.x * (256u * SCATTER_ITEMS) + threadIdx.x;
   uint4 t[SCATTER_ITEMS];
-  uint32_t start[SCATTER_ITEMS];
+  uint32_t start[SCATTER_ITEMS], slot[SCATTER_ITEMS];
   float4 r0[SCATTER_ITEMS];
   float2 r1[SCATTER_ITEMS];
 #pragma unroll
@@ -126,6 +126,9 @@ scatter_keys_kernel(const uint4* __restrict__ tmp, const uint2* __restrict__ ran
 #pragma unroll
   for (int u = 0; u < SCATTER_ITEMS; u++)
     if (i0 + 256u * u < R) {
+      // the slot inside the tile bucket: the histogram the preprocess built is counted back down (any order will do,
+      // the bucket is sorted next); the returning atomic is in flight while the reach mask is formed
+      slot[u] = atomicSub(&tile_count[t[u].z], 1u) - 1u;
       start[u] = ranges[t[u].z].x;
       if (PACK) {
         r0[u] = *reinterpret_cast<const float4*>(rec + (size_t)t[u].x * REC_FLOATS);
@@ -140,7 +143,7 @@ scatter_keys_kernel(const uint4* __restrict__ tmp, const uint2* __restrict__ ran
         const int tile_px = (int)(t[u].z % (uint32_t)gx) * SFGS_TILE, tile_py = (int)(t[u].z / (uint32_t)gx) * SFGS_TILE;
         lo = (t[u].x << 8) | reach_mask(r0[u].x, r0[u].y, r0[u].z, r0[u].w, r1[u].x, r1[u].y, tile_px, tile_py);
       }
-      keys[start[u] + t[u].w] = ((uint64_t)t[u].y << 32) | lo;
+      keys[start[u] + slot[u]] = ((uint64_t)t[u].y << 32) | lo;
     }
 }
 
@@ -428,32 +431,36 @@ tile_sort_warp_kernel(int tiles, const uint2* __restrict__ ranges, const uint32_
   emit_sorted<PACK, 32, true>(buf, bucket, n, lane, rg.x, point_list, inst_mask, rec, tile, gx);
 }
 
-// ---- longer lists: one CTA per tile, a small persistent grid strides over the tiles ------------------------------------
+// ---- longer lists: one CTA of 256 threads per tile, a small persistent grid strides over the tiles ----------------------
 // (a grid of one CTA per tile costs ~8 us of CTA launches even when no tile of the class exists — ncu, round 2b — and
-// the benchmark frames have none; here the CTAs of a class return after one header read in that case)
-template <int THREADS, int WINDOW, int MIN_N, bool PACK>
-__global__ void __launch_bounds__(THREADS, THREADS == 256 ? 3 : 8)
+// the benchmark frames have none; here the CTAs return after one header read in that case).  Lists of 513..1024 keys
+// are sorted with 4 keys per thread, 1025..4096 with 16, longer ones by the global radix fallback.
+constexpr int CS_THREADS = 256;
+constexpr int CS_WINDOW = 4096;
+template <bool PACK>
+__global__ void __launch_bounds__(CS_THREADS, 3)
 tile_sort_kernel(int tiles, const uint2* __restrict__ ranges, const uint32_t* __restrict__ hdr, uint64_t* __restrict__ keys,
                  uint64_t* __restrict__ keys_tmp, uint32_t* __restrict__ point_list,
                  const float* __restrict__ rec, int gx, unsigned char* __restrict__ inst_mask) {
-  if (hdr[HDR_OVERFLOW] || hdr[HDR_MAXTILE] <= (uint32_t)MIN_N) return;   // no tile of this class in the frame
+  if (hdr[HDR_OVERFLOW] || hdr[HDR_MAXTILE] <= (uint32_t)WS_MAX) return;   // every list is in the warp class
   extern __shared__ __align__(16) unsigned char sort_smem[];
-  // [PADIDX(WINDOW)] keys + [THREADS + 1] splits; the oversized-tile radix path reuses the space as 2560 scratch words
+  // [PADIDX(CS_WINDOW)] keys + [CS_THREADS + 1] splits; the oversized-tile radix path reuses the space as 2560 scratch words
   uint64_t* s = reinterpret_cast<uint64_t*>(sort_smem);
-  int* s_lo = reinterpret_cast<int*>(s + WINDOW + WINDOW / 16);
+  int* s_lo = reinterpret_cast<int*>(s + CS_WINDOW + CS_WINDOW / 16);
   for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {     // block-uniform
     const uint2 rg = ranges[tile];
     const int n = (int)(rg.y - rg.x);
-    if (n <= MIN_N || (THREADS != 256 && n > WINDOW)) continue;   // other class's tile (or empty)
+    if (n <= WS_MAX) continue;                                       // warp class (or empty)
     uint64_t* bucket = keys + rg.x;
-    if (n <= WINDOW) {
-      merge_sort_smem<THREADS, WINDOW / THREADS>(s, s_lo, bucket, n);
-      emit_sorted<PACK, THREADS, true>(s, bucket, n, threadIdx.x, rg.x, point_list, inst_mask, rec, tile, gx);
-    } else if (THREADS == 256) {
+    if (n <= CS_WINDOW) {
+      if (n <= CS_THREADS * 4) merge_sort_smem<CS_THREADS, 4>(s, s_lo, bucket, n);
+      else merge_sort_smem<CS_THREADS, 16>(s, s_lo, bucket, n);
+      emit_sorted<PACK, CS_THREADS, true>(s, bucket, n, threadIdx.x, rg.x, point_list, inst_mask, rec, tile, gx);
+    } else {
       radix_global(bucket, keys_tmp + rg.x, n, reinterpret_cast<uint32_t*>(s));
-      emit_sorted<PACK, THREADS, false>(bucket, bucket, n, threadIdx.x, rg.x, point_list, inst_mask, rec, tile, gx);
+      emit_sorted<PACK, CS_THREADS, false>(bucket, bucket, n, threadIdx.x, rg.x, point_list, inst_mask, rec, tile, gx);
     }
-    __syncthreads();     // the shared buffers are reused by the next tile
+    __syncthreads();     // the shared buffer is reused by the next tile
   }
 }
 
@@ -474,35 +481,31 @@ void sfgs_launch_scatter(const GeomLayout& g, const ImageLayout& im, const Binni
   // instances per thread of the mask-forming scatter (default 2; SFGS_SCATTER_ITEMS=1|2|4 for A/B measurements)
   static const int items = [] { const char* e = getenv("SFGS_SCATTER_ITEMS"); return e ? atoi(e) : 2; }();
   auto blocks_for = [&](int it) { return (unsigned)((capacity + 256ull * it - 1) / (256ull * it)); };
-  if (!sfgs_keys_packed(P)) scatter_keys_kernel<false, 4><<<blocks_for(4), 256, 0, st>>>(b.tmp, im.ranges, im.hdr, g.rec, im.tiles_x, b.keys);
-  else if (items == 4) scatter_keys_kernel<true, 4><<<blocks_for(4), 256, 0, st>>>(b.tmp, im.ranges, im.hdr, g.rec, im.tiles_x, b.keys);
-  else if (items == 2) scatter_keys_kernel<true, 2><<<blocks_for(2), 256, 0, st>>>(b.tmp, im.ranges, im.hdr, g.rec, im.tiles_x, b.keys);
-  else scatter_keys_kernel<true, 1><<<blocks_for(1), 256, 0, st>>>(b.tmp, im.ranges, im.hdr, g.rec, im.tiles_x, b.keys);
+  if (!sfgs_keys_packed(P)) scatter_keys_kernel<false, 4><<<blocks_for(4), 256, 0, st>>>(b.tmp, im.ranges, im.tile_count, im.hdr, g.rec, im.tiles_x, b.keys);
+  else if (items == 4) scatter_keys_kernel<true, 4><<<blocks_for(4), 256, 0, st>>>(b.tmp, im.ranges, im.tile_count, im.hdr, g.rec, im.tiles_x, b.keys);
+  else if (items == 2) scatter_keys_kernel<true, 2><<<blocks_for(2), 256, 0, st>>>(b.tmp, im.ranges, im.tile_count, im.hdr, g.rec, im.tiles_x, b.keys);
+  else scatter_keys_kernel<true, 1><<<blocks_for(1), 256, 0, st>>>(b.tmp, im.ranges, im.tile_count, im.hdr, g.rec, im.tiles_x, b.keys);
 }
 
 template <bool PACK>
 static void launch_tile_sorts(const GeomLayout& g, const ImageLayout& im, const BinningLayout& b, cudaStream_t st) {
-  constexpr size_t smem_mid = (1024 + 1024 / 16) * sizeof(uint64_t) + (128 + 1) * sizeof(int),
-                   smem_heavy = (4096 + 4096 / 16) * sizeof(uint64_t) + (256 + 1) * sizeof(int);
+  constexpr size_t smem_cta = (CS_WINDOW + CS_WINDOW / 16) * sizeof(uint64_t) + (CS_THREADS + 1) * sizeof(int);
   static SfgsPerDeviceOnce attr_once;   // function attributes are per device
   if (attr_once.first_use()) {
-    cudaFuncSetAttribute(tile_sort_kernel<256, 4096, 1024, PACK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_heavy);
+    cudaFuncSetAttribute(tile_sort_kernel<PACK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cta);
   }
   SFGS_COUNT_LAUNCH();
   tile_sort_warp_kernel<PACK><<<(im.tiles + WS_WARPS - 1) / WS_WARPS, WS_WARPS * 32, 0, st>>>(
       im.tiles, im.ranges, im.hdr, b.keys, b.point_list, g.rec, im.tiles_x, b.inst_mask);
-  // the CTA-wide classes: persistent grids (resident CTAs of each kernel on every SM), returning at once when the
-  // frame's longest list (header word written by the scan) is below the class
+  // lists beyond the warp class: a persistent grid (three resident CTAs per SM) that returns at once when the frame's
+  // longest list (header word written by the scan) is inside the warp class
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   { int v = 0; if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0) sms = v; }
-  const int grid_mid = im.tiles < 8 * sms ? im.tiles : 8 * sms, grid_heavy = im.tiles < 3 * sms ? im.tiles : 3 * sms;
+  const int grid_cta = im.tiles < 3 * sms ? im.tiles : 3 * sms;
   SFGS_COUNT_LAUNCH();
-  tile_sort_kernel<128, 1024, WS_MAX, PACK><<<grid_mid, 128, smem_mid, st>>>(im.tiles, im.ranges, im.hdr, b.keys, b.keys_tmp,
-                                                                             b.point_list, g.rec, im.tiles_x, b.inst_mask);
-  SFGS_COUNT_LAUNCH();
-  tile_sort_kernel<256, 4096, 1024, PACK><<<grid_heavy, 256, smem_heavy, st>>>(im.tiles, im.ranges, im.hdr, b.keys, b.keys_tmp,
-                                                                               b.point_list, g.rec, im.tiles_x, b.inst_mask);
+  tile_sort_kernel<PACK><<<grid_cta, CS_THREADS, smem_cta, st>>>(im.tiles, im.ranges, im.hdr, b.keys, b.keys_tmp, b.point_list,
+                                                                  g.rec, im.tiles_x, b.inst_mask);
 }
 
 void sfgs_launch_tile_sort(const GeomLayout& g, const ImageLayout& im, const BinningLayout& b, int P, cudaStream_t st) {

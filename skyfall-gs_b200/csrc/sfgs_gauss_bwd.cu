@@ -12,6 +12,7 @@
 // Gaussians — compacted into dense warps — run the adjoint chain and overwrite
 // their rows.
 #include "sfgs_common.cuh"
+#include <cstdlib>
 
 namespace {
 
@@ -35,8 +36,8 @@ __device__ __forceinline__ float3 dnormvdv3(float3 v, float3 dv) {
   return o;
 }
 
-template <bool WRITE_SH>
-__global__ void __launch_bounds__(GB_THREADS, 5)
+template <bool WRITE_SH, int MIN_CTAS>
+__global__ void __launch_bounds__(GB_THREADS, MIN_CTAS)
 gauss_bwd_kernel(int g_begin, int g_end, int acc_row0, int D, int M, const float* __restrict__ means3D, const int* __restrict__ radii,
                  const float* __restrict__ shs, const unsigned char* __restrict__ clamped,
                  const float* __restrict__ scales, const float* __restrict__ rotations, float scale_modifier,
@@ -501,7 +502,14 @@ void sfgs_launch_gauss_bwd(const sfgs_backward_args* a, const GeomLayout& g, flo
       a->scale_modifier, cov3D_ptr, g.rec, a->norm3D_precomp, a->viewmatrix, a->projmatrix, focal_x, focal_y,         \
       a->tan_fovx, a->tan_fovy, a->kernel_size, a->cam_pos, acc, a->dL_dmean2D, a->dL_dconic, a->dL_dopacity,         \
       a->dL_dcolor, a->dL_ddepth, a->dL_dmean3D, a->dL_dcov3D, a->dL_dnorm3D, a->dL_dsh, a->dL_dscale, a->dL_drot
-  if (a->M > 0 && a->dL_dsh != nullptr) gauss_bwd_kernel<true><<<blocks, GB_THREADS, 0, st>>>(GB_ARGS);
-  else gauss_bwd_kernel<false><<<blocks, GB_THREADS, 0, st>>>(GB_ARGS);
+  // experiment switch: SFGS_GB_CTAS=5|6|7 resident CTAs per SM for the SH-writing variant (96 / 80 / 72 registers)
+  static const int ctas = [] { const char* e = getenv("SFGS_GB_CTAS"); return e ? atoi(e) : 5; }();
+  if (a->M > 0 && a->dL_dsh != nullptr) {
+    if (ctas == 7) gauss_bwd_kernel<true, 7><<<blocks, GB_THREADS, 0, st>>>(GB_ARGS);
+    else if (ctas == 6) gauss_bwd_kernel<true, 6><<<blocks, GB_THREADS, 0, st>>>(GB_ARGS);
+    else gauss_bwd_kernel<true, 5><<<blocks, GB_THREADS, 0, st>>>(GB_ARGS);
+  } else {
+    gauss_bwd_kernel<false, 5><<<blocks, GB_THREADS, 0, st>>>(GB_ARGS);
+  }
 #undef GB_ARGS
 }

@@ -327,6 +327,12 @@ preprocess_kernel(int P, int D, int M,
     float vis_depth = 0.f;
     int out_radius = 0;
     uint32_t out_tiles = 0;
+    // results of the geometry half that the colour half and the record stores need
+    bool visible = false;
+    float px = 0.f, py = 0.f, pz = 0.f, sx = 0.f, sy = 0.f, sz = 0.f, opac_in = 0.f;
+    float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+    float g_pix_x = 0.f, g_pix_y = 0.f, g_conx = 0.f, g_cony = 0.f, g_conz = 0.f, g_coef = 0.f;
+    Sym3 g_V = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 
     if (in_range) {
       if (sh_staged) {
@@ -339,14 +345,12 @@ preprocess_kernel(int P, int D, int M,
           }
         asm volatile("cp.async.commit_group;\n" ::);
       }
-      const float px = means3D[3 * (size_t)idx], py = means3D[3 * (size_t)idx + 1], pz = means3D[3 * (size_t)idx + 2];
-      float sx = 0.f, sy = 0.f, sz = 0.f;
-      float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+      px = means3D[3 * (size_t)idx]; py = means3D[3 * (size_t)idx + 1]; pz = means3D[3 * (size_t)idx + 2];
       if (need_sr) {
         sx = scales[3 * (size_t)idx]; sy = scales[3 * (size_t)idx + 1]; sz = scales[3 * (size_t)idx + 2];
         q = *reinterpret_cast<const float4*>(rotations + 4 * (size_t)idx);
       }
-      const float opac_in = opacities[idx];
+      opac_in = opacities[idx];
       const float view_z = vm[2] * px + vm[6] * py + vm[10] * pz + vm[14];
       if (view_z > 0.2f) {
         const float hx = pm[0] * px + pm[4] * py + pm[8] * pz + pm[12];
@@ -381,39 +385,9 @@ preprocess_kernel(int P, int D, int M,
           rb.y0 = max(r.y0, band0); rb.y1 = min(r.y1, band1);
           const uint32_t ntiles = rb.y1 > rb.y0 ? (uint32_t)((rb.x1 - rb.x0) * (rb.y1 - rb.y0)) : 0u;
           if (ntiles_full != 0) {
-            if (cov3D_precomp == nullptr) {
-              float* co = cov3D_out + 6 * (size_t)idx;
-              co[0] = V.c0; co[1] = V.c1; co[2] = V.c2; co[3] = V.c3; co[4] = V.c4; co[5] = V.c5;
-            }
-            float n[3];
-            if (norm3D_precomp != nullptr) {
-              n[0] = norm3D_precomp[3 * (size_t)idx]; n[1] = norm3D_precomp[3 * (size_t)idx + 1]; n[2] = norm3D_precomp[3 * (size_t)idx + 2];
-            } else {
-              normal_from_scale_rot(sx, sy, sz, q.x, q.y, q.z, q.w, px, py, pz, cam_pos[0], cam_pos[1], cam_pos[2], n);
-            }
-            float rgb[3];
-            unsigned cmask = 0;
-            if (colors_precomp == nullptr) {
-              if (sh_staged) {
-                asm volatile("cp.async.wait_group 0;\n" ::: "memory");
-                // coefficient j sits in word (j & 3) of float4 [j >> 2][tid] of this thread's shared-memory column
-                const float* col = reinterpret_cast<const float*>(s_sh) + 4 * tid;
-                sh_to_rgb(D, [&](int j) { return col[(j >> 2) * (4 * PRE_THREADS) + (j & 3)]; }, px, py, pz, cam_pos[0],
-                          cam_pos[1], cam_pos[2], rgb, cmask);
-              } else {
-                const float* shp = shs + (size_t)idx * M * 3;
-                sh_to_rgb(D, [&](int j) { return shp[j]; }, px, py, pz, cam_pos[0], cam_pos[1], cam_pos[2], rgb, cmask);
-              }
-            } else {
-              rgb[0] = colors_precomp[3 * (size_t)idx]; rgb[1] = colors_precomp[3 * (size_t)idx + 1]; rgb[2] = colors_precomp[3 * (size_t)idx + 2];
-            }
-            clamped[idx] = (unsigned char)cmask;
-
-            float4* o = reinterpret_cast<float4*>(rec + (size_t)idx * REC_FLOATS);
-            o[0] = make_float4(pix_x, pix_y, conx, cony);
-            o[1] = make_float4(conz, opac_in * cov.w, view_z, 0.f);
-            o[2] = make_float4(rgb[0], rgb[1], rgb[2], n[0]);
-            o[3] = make_float4(n[1], n[2], 0.f, 0.f);
+            visible = true;
+            g_pix_x = pix_x; g_pix_y = pix_y; g_conx = conx; g_cony = cony; g_conz = conz; g_coef = cov.w;
+            g_V = V;
             out_radius = iradius;
             out_tiles = ntiles;
             vis_rect = rb;
@@ -421,59 +395,83 @@ preprocess_kernel(int P, int D, int M,
           }
         }
       }
-      radii[idx] = out_radius;
-      tiles_touched[idx] = out_tiles;
     }
-    // ---- append this warp's tile instances to the unsorted list -----------------------------------
-    // One warp-aggregated atomic reserves the slots.  The warp's instances are then dealt out to the
-    // lanes round-robin (instance j -> owner found by a binary search over the inclusive prefix kept in
-    // shared memory), so a large splat no longer serialises its lane and 32 independent histogram
-    // atomics are in flight per step.  The histogram atomic (it replaces the per-Gaussian prefix sum of
-    // the reference) hands back the instance's slot inside its tile bucket: the later scatter needs none.
-    asm volatile("cp.async.wait_group 0;\n" ::: "memory");   // culled threads may still have copies in flight
+    // ---- reserve this warp's slots of the unsorted instance list NOW: the returning atomic travels to L2 and back
+    // while the normals and colours below are evaluated (it used to be issued after them and waited for in place)
     uint32_t incl = out_tiles;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= (unsigned)o) incl += y; }
     const uint32_t warp_total = __shfl_sync(0xffffffffu, incl, 31);
+    uint32_t warp_base = 0;
+    if (warp_total != 0 && lane == 31) warp_base = atomicAdd(&hdr[HDR_TMP_COUNT], warp_total);
+
+    if (in_range) {
+      if (visible) {
+        if (cov3D_precomp == nullptr) {
+          float* co = cov3D_out + 6 * (size_t)idx;
+          co[0] = g_V.c0; co[1] = g_V.c1; co[2] = g_V.c2; co[3] = g_V.c3; co[4] = g_V.c4; co[5] = g_V.c5;
+        }
+        float n[3];
+        if (norm3D_precomp != nullptr) {
+          n[0] = norm3D_precomp[3 * (size_t)idx]; n[1] = norm3D_precomp[3 * (size_t)idx + 1]; n[2] = norm3D_precomp[3 * (size_t)idx + 2];
+        } else {
+          normal_from_scale_rot(sx, sy, sz, q.x, q.y, q.z, q.w, px, py, pz, cam_pos[0], cam_pos[1], cam_pos[2], n);
+        }
+        float rgb[3];
+        unsigned cmask = 0;
+        if (colors_precomp == nullptr) {
+          if (sh_staged) {
+            asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+            // coefficient j sits in word (j & 3) of float4 [j >> 2][tid] of this thread's shared-memory column
+            const float* col = reinterpret_cast<const float*>(s_sh) + 4 * tid;
+            sh_to_rgb(D, [&](int j) { return col[(j >> 2) * (4 * PRE_THREADS) + (j & 3)]; }, px, py, pz, cam_pos[0],
+                      cam_pos[1], cam_pos[2], rgb, cmask);
+          } else {
+            const float* shp = shs + (size_t)idx * M * 3;
+            sh_to_rgb(D, [&](int j) { return shp[j]; }, px, py, pz, cam_pos[0], cam_pos[1], cam_pos[2], rgb, cmask);
+          }
+        } else {
+          rgb[0] = colors_precomp[3 * (size_t)idx]; rgb[1] = colors_precomp[3 * (size_t)idx + 1]; rgb[2] = colors_precomp[3 * (size_t)idx + 2];
+        }
+        clamped[idx] = (unsigned char)cmask;
+
+        float4* o = reinterpret_cast<float4*>(rec + (size_t)idx * REC_FLOATS);
+        o[0] = make_float4(g_pix_x, g_pix_y, g_conx, g_cony);
+        o[1] = make_float4(g_conz, opac_in * g_coef, vis_depth, 0.f);
+        o[2] = make_float4(rgb[0], rgb[1], rgb[2], n[0]);
+        o[3] = make_float4(n[1], n[2], 0.f, 0.f);
+      }
+      radii[idx] = out_radius;
+      tiles_touched[idx] = out_tiles;
+    }
+    // ---- append this warp's tile instances to the unsorted list -----------------------------------
+    // The warp's instances are dealt out to the lanes round-robin (instance j -> owner found by a binary search over
+    // the inclusive prefix kept in shared memory), so a large splat does not serialise its lane.  The histogram
+    // update (it replaces the per-Gaussian prefix sum of the reference) is a fire-and-forget reduction: nothing in
+    // this kernel waits for L2 any more — the slot inside the tile bucket is handed out by the key scatter, which
+    // counts the same histogram back down (round 2a took the slot from a RETURNING atomic here and stalled on it:
+    // 38 % of this kernel's warp-stall samples sat in this loop).
+    asm volatile("cp.async.wait_group 0;\n" ::: "memory");   // culled threads may still have copies in flight
     if (warp_total != 0) {
-      uint32_t warp_base = 0;
-      if (lane == 31) warp_base = atomicAdd(&hdr[HDR_TMP_COUNT], warp_total);
       warp_base = __shfl_sync(0xffffffffu, warp_base, 31);
       s_incl[tid] = incl;
       s_rect[tid] = make_int4(vis_rect.x0, vis_rect.y0, vis_rect.x1 - vis_rect.x0, (int)__float_as_uint(vis_depth));
       s_gid[tid] = (uint32_t)idx;
       __syncwarp();
-      // four instances per lane and step, so four histogram atomics are in flight before the first result is needed
-      constexpr int APP = 4;
-      for (uint32_t j0 = lane; j0 < warp_total; j0 += 32 * APP) {
-        uint32_t t[APP], gid[APP], dep[APP], pos[APP];
+      for (uint32_t j = lane; j < warp_total; j += 32) {
+        // owner = first lane whose inclusive prefix exceeds j
+        int lo = 0;
 #pragma unroll
-        for (int u = 0; u < APP; u++) {
-          const uint32_t j = j0 + 32u * u;
-          t[u] = 0xffffffffu;
-          if (j < warp_total) {
-            // owner = first lane whose inclusive prefix exceeds j
-            int lo = 0;
-#pragma unroll
-            for (int step = 16; step > 0; step >>= 1)
-              if (s_incl[wbase + lo + step - 1] <= j) lo += step;
-            const uint32_t excl = lo > 0 ? s_incl[wbase + lo - 1] : 0u;
-            const int4 rc = s_rect[wbase + lo];
-            const uint32_t kk = j - excl;                      // kk-th tile of the owner's rectangle, row-major
-            const uint32_t ty = kk / (uint32_t)rc.z, tx = kk - ty * (uint32_t)rc.z;
-            t[u] = (uint32_t)(rc.y + (int)ty) * (uint32_t)gx + (uint32_t)(rc.x + (int)tx);
-            gid[u] = s_gid[wbase + lo];
-            dep[u] = (uint32_t)rc.w;
-          }
-        }
-#pragma unroll
-        for (int u = 0; u < APP; u++)
-          if (t[u] != 0xffffffffu) pos[u] = atomicAdd(&tile_count[t[u]], 1u);
-#pragma unroll
-        for (int u = 0; u < APP; u++) {
-          const unsigned long long slot = (unsigned long long)warp_base + j0 + 32u * u;
-          if (t[u] != 0xffffffffu && slot < capacity) tmp[slot] = make_uint4(gid[u], dep[u], t[u], pos[u]);
-        }
+        for (int step = 16; step > 0; step >>= 1)
+          if (s_incl[wbase + lo + step - 1] <= j) lo += step;
+        const uint32_t excl = lo > 0 ? s_incl[wbase + lo - 1] : 0u;
+        const int4 rc = s_rect[wbase + lo];
+        const uint32_t kk = j - excl;                      // kk-th tile of the owner's rectangle, row-major
+        const uint32_t ty = kk / (uint32_t)rc.z, tx = kk - ty * (uint32_t)rc.z;
+        const uint32_t tile = (uint32_t)(rc.y + (int)ty) * (uint32_t)gx + (uint32_t)(rc.x + (int)tx);
+        atomicAdd(&tile_count[tile], 1u);                  // result unused: RED
+        const unsigned long long slot = (unsigned long long)warp_base + j;
+        if (slot < capacity) tmp[slot] = make_uint4(s_gid[wbase + lo], (uint32_t)rc.w, tile, 0u);
       }
       __syncwarp();     // the warp's shared rows are rewritten by its next pass
     }
