@@ -502,12 +502,11 @@ void sfgs_launch_gauss_bwd(const sfgs_backward_args* a, const GeomLayout& g, flo
       a->scale_modifier, cov3D_ptr, g.rec, a->norm3D_precomp, a->viewmatrix, a->projmatrix, focal_x, focal_y,         \
       a->tan_fovx, a->tan_fovy, a->kernel_size, a->cam_pos, acc, a->dL_dmean2D, a->dL_dconic, a->dL_dopacity,         \
       a->dL_dcolor, a->dL_ddepth, a->dL_dmean3D, a->dL_dcov3D, a->dL_dnorm3D, a->dL_dsh, a->dL_dscale, a->dL_drot
-  // experiment switch: SFGS_GB_CTAS=5|6|7 resident CTAs per SM for the SH-writing variant (96 / 80 / 72 registers)
-  static const int ctas = [] { const char* e = getenv("SFGS_GB_CTAS"); return e ? atoi(e) : 5; }();
+  // resident CTAs per SM of the SH-writing variant: 5 (96 registers).  Measured on the benchmark frame: 6 / 7 CTAs (80 / 72
+  // registers, 100-180 bytes of spills) take 0.152 / 0.170 ms instead of 0.131, 4 CTAs (127 registers) 0.128 ms; issuing
+  // the first pass's loads before the zero fill (to overlap their round trip with the fill's stores) 0.134 ms.
   if (a->M > 0 && a->dL_dsh != nullptr) {
-    if (ctas == 7) gauss_bwd_kernel<true, 7><<<blocks, GB_THREADS, 0, st>>>(GB_ARGS);
-    else if (ctas == 6) gauss_bwd_kernel<true, 6><<<blocks, GB_THREADS, 0, st>>>(GB_ARGS);
-    else gauss_bwd_kernel<true, 5><<<blocks, GB_THREADS, 0, st>>>(GB_ARGS);
+    gauss_bwd_kernel<true, 5><<<blocks, GB_THREADS, 0, st>>>(GB_ARGS);
   } else {
     gauss_bwd_kernel<false, 5><<<blocks, GB_THREADS, 0, st>>>(GB_ARGS);
   }
