@@ -276,26 +276,50 @@ def run_tilerows(P, extent, rank, world, dev, steps, warmup):
                 print(f"[tilerows] symmetric memory unavailable ({type(exc).__name__}: {exc}); using NCCL", file=sys.stderr)
 
     multi = world > 1
-    for _ in range(warmup):
-        step()
-    if multi:
-        dist.barrier()
-    torch.cuda.synchronize(dev)
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     import time
-    a.record()
-    t_host = time.perf_counter()
-    for _ in range(steps):
-        step()
-    t_host = (time.perf_counter() - t_host) * 1e3 / steps      # host time to ISSUE a step (incl. the forward's one wait)
-    b.record()
-    if multi:
-        dist.barrier()
-    torch.cuda.synchronize(dev)
-    ms = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
-    if multi:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    total = float(ms.item())
+
+    def timed_pass(nwarm):
+        """One pass of `steps` steps: CUDA events around the WHOLE loop (what is reported) and around every step (only to
+        tell whether the pass was disturbed from outside).  Returns (loop ms max over ranks, clean?, host issue ms/step)."""
+        for _ in range(nwarm):
+            step()
+        if multi:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        per = []
+        a.record()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            step()
+            e1.record()
+            per.append((e0, e1))
+        t_issue = (time.perf_counter() - t0) * 1e3 / steps    # host time to ISSUE a step (incl. the forward's one wait)
+        b.record()
+        if multi:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+        loop = a.elapsed_time(b)
+        fastest = min(x.elapsed_time(y) for x, y in per)
+        # the same rule as bench.py's headline: a pass whose mean step exceeds 1.05x its fastest step was disturbed (the
+        # boxes are shared: a descheduled host thread leaves the GPU idle inside the loop) and is measured again
+        v = torch.tensor([loop, 1.0 if loop / steps <= 1.05 * fastest else 0.0], dtype=torch.float64, device=dev)
+        if multi:
+            lo = v.clone()
+            dist.all_reduce(v, op=dist.ReduceOp.MAX)           # loop time: max over ranks
+            dist.all_reduce(lo, op=dist.ReduceOp.MIN)          # clean only if clean on every rank
+            v[1] = lo[1]
+        return float(v[0].item()), bool(v[1].item() == 1.0), t_issue
+
+    passes = []
+    for k in range(4):
+        passes.append(timed_pass(warmup if k == 0 else 3))
+        if passes[-1][1]:
+            break
+    clean = [p_ for p_ in passes if p_[1]]
+    total, _, t_host = clean[0] if clean else min(passes, key=lambda p_: p_[0])
     R_band = torch.tensor([float(last["R"])], dtype=torch.float64, device=dev)
     R_all = [torch.zeros_like(R_band) for _ in range(world)]
     if multi:
@@ -319,4 +343,7 @@ def run_tilerows(P, extent, rank, world, dev, steps, warmup):
             "steps": steps, "warmup": warmup,
             "parallelism": f"tilerows x{world}: {gather} + {collective}; each rank finishes the gradients of P/N Gaussians",
             "gather": gather, "collective": collective, "cuts": cuts,
-            "instances_per_band": [int(x.item()) for x in R_all], "timing": "CUDA events around the whole loop, max over ranks"}
+            "instances_per_band": [int(x.item()) for x in R_all],
+            "timing": "CUDA events around the whole loop of `steps` steps, max over ranks; a pass whose mean step exceeds 1.05x its "
+                      "fastest step (per-step events) is measured again, <= 4 passes",
+            "passes_ms_per_step": [round(p_[0] / steps, 4) for p_ in passes], "clean_pass_found": bool(clean)}
