@@ -232,10 +232,35 @@ def step_ref_stock(d, cam):
     return (num_rendered, color, depth, norm, alpha, radii), g
 
 
+def settle(step_fn, flush, dev, min_seconds=0.5, max_seconds=3.0):
+    """UNTIMED extra warm-up after the W requested steps.  A freshly set-up loop (or one resumed after the GPU sat idle
+    while the host prepared the next scene) runs its first 0.1-0.3 s in a slow mode on these boxes — steps of 5-8 ms,
+    sometimes bursts of 20-40 ms, then 1.08 ms flat for good (gpurun_out/v1_bench.err, v3_bench.err) — which five
+    warm-up steps do not outlast.  So steps are run four at a time for at least `min_seconds` of wall clock and until a
+    group is within 5 % of the fastest group seen (at most `max_seconds`).  Nothing here is reported."""
+    best, n, t0 = None, 0, time.perf_counter()
+    while True:
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(4):
+            flush()
+            step_fn()
+        b.record()
+        torch.cuda.synchronize(dev)
+        t = a.elapsed_time(b)
+        n += 4
+        el = time.perf_counter() - t0
+        if el >= max_seconds or (el >= min_seconds and best is not None and t <= 1.05 * best):
+            break
+        best = t if best is None else min(best, t)
+    return n
+
+
 def timed_steps(step_fn, steps, warmup, flush, dev, between=None):
     for _ in range(warmup):
         step_fn()
     torch.cuda.synchronize(dev)
+    settle(step_fn, flush, dev)
     evs = []
     for i in range(steps):
         if between is not None and i % 4 == 2:
@@ -255,7 +280,7 @@ def timed_steps(step_fn, steps, warmup, flush, dev, between=None):
     return ms
 
 
-def measure(step_fn, steps, warmup, flush, dev, between=None, max_attempts=5):
+def measure(step_fn, steps, warmup, flush, dev, between=None, max_attempts=8):
     """Time exactly `steps` steps; a pass disturbed from outside is rejected and re-measured.
 
     Every step launches ~10 kernels from Python and the forward waits once for the instance count, so a host
@@ -263,7 +288,8 @@ def measure(step_fn, steps, warmup, flush, dev, between=None, max_attempts=5):
     (load average 40-60 on 128 cores observed) and single steps of 5-250 ms appear at random in either leg.
     A pass counts as clean when its MEAN step is within 5 % of its fastest step (one large spike is enough to
     fail it); the reported pass is the first clean one, or the pass with the smallest total if none of
-    `max_attempts` is.  Every attempt is listed in the JSON line."""
+    `max_attempts` is.  Every attempt is listed in the JSON line.  Each pass starts with W untimed warm-up steps and the
+    untimed `settle` loop above."""
     attempts = []
     for k in range(max_attempts):
         ms = timed_steps(step_fn, steps, warmup if k == 0 else 3, flush, dev, between)
@@ -407,7 +433,7 @@ def frame_record(name, impl_kind, dev, steps):
     d = make_inputs(scene, cam, dev)
     flush = L2Flusher(dev)
     step = {"ours": lambda: step_ours(d, cam), "stock": lambda: step_ref_stock(d, cam), "shim": lambda: step_ref(d, cam)}[impl_kind]
-    ms, timing = measure(step, steps, 5, flush, dev, max_attempts=4)      # same disturbance rule as the headline
+    ms, timing = measure(step, steps, 5, flush, dev, max_attempts=6)      # same disturbance rule as the headline
     med = float(np.median(ms))
     f, _ = step()
     torch.cuda.synchronize(dev)
@@ -898,7 +924,7 @@ def main():
                    "d2h_bytes_per_step": 4},
            "clocks": clocks}
     out["timing"] = {"value": value_info, "e2e": e2e_info,
-                     "rule": "a pass whose mean step exceeds 1.05x its fastest step is re-measured (<= 5 passes)"}
+                     "rule": "W warm-up steps, then untimed steps in groups of 4 for >= 0.5 s and until a group is within 5 % of the fastest group (<= 3 s), then exactly K timed steps; a pass whose mean step exceeds 1.05x its fastest step is re-measured (<= 8 passes)"}
     out["e2e"]["api"] = {"ours": "diff_gauss.GaussianRasterizer + autograd (this library's drop-in package)",
                          "stock": "the reference's own diff_gauss.GaussianRasterizer + autograd over its own pybind module",
                          "shim": "reference CudaRasterizer::Rasterizer forward/backward behind the ctypes shim"}[kind]
