@@ -262,6 +262,31 @@ def test_long_tile_lists_use_both_sort_paths(cuda_device):
     assert t_ours <= 1.5 * t_ref + 0.2, (t_ours, t_ref)
 
 
+@pytest.mark.parametrize("n", [1, 2, 31, 33, 127, 128, 129, 255, 256, 257, 511, 512, 513, 1023, 1024, 1025, 4095, 4096, 4097])
+def test_sort_class_boundaries_and_depth_ties(cuda_device, n):
+    """ONE tile (a 16x16 image) whose list has exactly `n` instances, at every size-class boundary of the per-tile sort:
+    warp class with 4 / 8 / 16 keys per lane (<= 128 / 256 / 512), CTA class with 4 / 16 keys per thread (<= 1024 / 4096),
+    global radix beyond.  A third of the Gaussians are exact duplicates of others (what densification's clone step
+    produces): equal depths, so the order inside the tile is decided by the Gaussian id exactly like the reference's stable
+    radix sort decides it."""
+    if not ref_available():
+        pytest.skip("oracle/_ref not built")
+    from oracle import ref_cuda
+    dev = cuda_device
+    scene = S.blob_scene(n, seed=1000 + n, spread=0.05, scale=0.08)
+    dup = np.arange(n) % 3 == 2
+    scene.means3D[dup] = scene.means3D[np.maximum(np.flatnonzero(dup) - 1, 0)]      # exact copies: depth ties
+    cam = S.simple_camera(16, 16, distance=6.0)
+    d, bg_t, col, ours, ref = run_pair(scene, cam, dev, bg=(0, 0, 0))
+    oi, ri = Hh.our_internals(ours, scene.P, 16, 16), ref_cuda.internals(ref, scene.P, 16, 16)
+    assert int(ri["ranges"][0, 1] - ri["ranges"][0, 0]) == n == int(ref["num_rendered"]) == int(ours["num_rendered"])
+    assert torch.equal(oi["ranges"], ri["ranges"])
+    assert torch.equal(oi["point_list"][:n], ri["point_list"][:n])
+    assert torch.equal(oi["n_contrib"], ri["n_contrib"])
+    assert torch.equal(ours["depth"], ref["depth"]) and torch.equal(ours["alpha"], ref["alpha"])
+    assert (ours["color"] - ref["color"]).abs().max().item() <= IMG_ATOL
+
+
 def test_full_size_properties(cuda_device):
     """BASELINE configs[1] size (1M Gaussians, 1080p): size-independent invariants."""
     dev = cuda_device
