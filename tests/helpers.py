@@ -131,7 +131,9 @@ def adjudicate_gradients(d, cam, sh_degree, bg, I, out_alpha, radii, cot, ours, 
     in the mean, at the 99.9th percentile and in the worst element.  No element is exempt.
 
     I: forward intermediates in the reference's vocabulary (oracle.ref_cuda.internals or helpers.our_internals).
-    ref: one run of the reference's gradients, or a list of runs.
+    ref: one run of the reference's gradients, or a list of runs (every statistic: the largest over the runs).
+    ours: one run of this library's gradients, or a list of runs (mean / p99.9: the largest over the runs; the worst
+    element: the median over the runs — see oracle.adjudicator.error_report).
     Returns the report (also appended to gpurun_out/adjudication.jsonl when that directory exists)."""
     import json
     import os

@@ -89,9 +89,10 @@ def test_backward_vs_reference_adjudicated_by_float64(cuda_device, case):
     cot = [torch.from_numpy(c).to(dev) for c in S.cotangents(cam.width, cam.height, seed=4)]
     from oracle import ref_cuda
     gb = Hh.run_ours_backward(d, cam, scene.sh_degree, bg_t, ours, cot)
+    gbs = [gb] + [Hh.run_ours_backward(d, cam, scene.sh_degree, bg_t, ours, cot) for _ in range(2)]     # this library's reductions are unordered too
     r1 = [Hh.run_ref_backward(d, cam, scene.sh_degree, bg_t, ref, cot) for _ in range(3)]
     ri = ref_cuda.internals(ref, scene.P, cam.height, cam.width)
-    Hh.adjudicate_gradients(d, cam, scene.sh_degree, bg_t, ri, ref["alpha"], ref["radii"], cot, gb, r1,
+    Hh.adjudicate_gradients(d, cam, scene.sh_degree, bg_t, ri, ref["alpha"], ref["radii"], cot, gbs, r1,
                             f"backward_vs_reference[{case}]")
     # culled Gaussians get exact zeros
     inv = ours["radii"] == 0
@@ -126,9 +127,10 @@ def test_randomised_differential_vs_reference(cuda_device, seed):
         assert (ours[k] - ref[k]).abs().max().item() <= IMG_ATOL, k
     cot = [torch.from_numpy(c).to(dev) for c in S.cotangents(W, H, seed=seed)]
     gb = Hh.run_ours_backward(d, cam, deg, bg_t, ours, cot, kernel_size=kw["kernel_size"], scale_modifier=kw["scale_modifier"])
+    gbs = [gb] + [Hh.run_ours_backward(d, cam, deg, bg_t, ours, cot, kernel_size=kw["kernel_size"], scale_modifier=kw["scale_modifier"]) for _ in range(2)]     # this library's reductions are unordered too
     r1 = [Hh.run_ref_backward(d, cam, deg, bg_t, ref, cot, kernel_size=kw["kernel_size"],
                               scale_modifier=kw["scale_modifier"]) for _ in range(3)]
-    Hh.adjudicate_gradients(d, cam, deg, bg_t, ri, ref["alpha"], ref["radii"], cot, gb, r1, f"randomised[{seed}]",
+    Hh.adjudicate_gradients(d, cam, deg, bg_t, ri, ref["alpha"], ref["radii"], cot, gbs, r1, f"randomised[{seed}]",
                             kernel_size=kw["kernel_size"], scale_modifier=kw["scale_modifier"])
 
 
@@ -156,13 +158,22 @@ def test_against_golden_fixtures(cuda_device, name):
     cot = [torch.from_numpy(c).to(dev) for c in kw["cot"]]
     gb = Hh.run_ours_backward(d, cam, kw["sh_degree"], bg_t, f, cot, kernel_size=kw["kernel_size"],
                               scale_modifier=kw["scale_modifier"], colors=col)
+    gbs = [gb] + [Hh.run_ours_backward(d, cam, kw["sh_degree"], bg_t, f, cot, kernel_size=kw["kernel_size"],
+                              scale_modifier=kw["scale_modifier"], colors=col) for _ in range(2)]     # this library's reductions are unordered too
     # the fixture holds one run of the reference CUDA build's gradients; whose error a deviation is, is decided by
     # the float64 adjudicator on this library's forward intermediates (asserted bit-identical on indexing above)
     ref_g = {k: torch.from_numpy(g["grad_" + k]).to(dev) for k in ("means2D", "colors", "opacity", "means3D", "cov3D",
                                                                   "norm3D", "sh", "scales", "rot")}
     # (one stored run of a non-deterministic reference: its worst element is a single draw of an extreme-value
-    # statistic, so only that factor is wider here than in the live tests, which take the worst of three runs)
-    Hh.adjudicate_gradients(d, cam, kw["sh_degree"], bg_t, it, f["alpha"], f["radii"], cot, gb, ref_g,
+    # statistic — on blob_sh3 this library's own worst `means3D` element ranges from 3.6e-4 to 2.1e-3 over eight runs —
+    # so that factor is wider here than in the live tests, and where the reference build travels with the snapshot its
+    # live gradients of the same case join the stored run: every reference statistic is the largest over the runs)
+    if ref_available():
+        fr = Hh.run_ref_forward(d, cam, kw["sh_degree"], bg_t, kernel_size=kw["kernel_size"],
+                                scale_modifier=kw["scale_modifier"], colors=col)
+        ref_g = [ref_g] + [Hh.run_ref_backward(d, cam, kw["sh_degree"], bg_t, fr, cot, kernel_size=kw["kernel_size"],
+                                               scale_modifier=kw["scale_modifier"], colors=col) for _ in range(3)]
+    Hh.adjudicate_gradients(d, cam, kw["sh_degree"], bg_t, it, f["alpha"], f["radii"], cot, gbs, ref_g,
                             f"golden[{name}]", kernel_size=kw["kernel_size"], scale_modifier=kw["scale_modifier"],
                             colors=col, factors={"mean": 1.5, "p999": 2.0, "max": 8.0})
 
@@ -631,8 +642,9 @@ def test_benched_configurations_vs_reference(cuda_device, name):
     del oi
     cot = [torch.from_numpy(c).to(dev) for c in S.cotangents(W, H, seed=1)]      # bench.py's cotangents
     gb = Hh.run_ours_backward(d, cam, scene.sh_degree, bg_t, ours, cot)
+    gbs = [gb] + [Hh.run_ours_backward(d, cam, scene.sh_degree, bg_t, ours, cot) for _ in range(2)]     # this library's reductions are unordered too
     r1 = [Hh.run_ref_backward(d, cam, scene.sh_degree, bg_t, ref, cot) for _ in range(3)]
-    Hh.adjudicate_gradients(d, cam, scene.sh_degree, bg_t, ri, ref["alpha"], ref["radii"], cot, gb, r1, name)
+    Hh.adjudicate_gradients(d, cam, scene.sh_degree, bg_t, ri, ref["alpha"], ref["radii"], cot, gbs, r1, name)
     inv = ours["radii"] == 0
     for k in ("means2D", "opacity", "means3D", "sh", "scales", "rot"):
         assert gb[k][inv].abs().max().item() == 0.0, k       # culled Gaussians get exact zeros
@@ -664,8 +676,9 @@ def test_long_thin_splats_crossing_many_tiles(cuda_device):
             assert (ours[k] - ref[k]).abs().max().item() <= IMG_ATOL, (k, ks)
         cot = [torch.from_numpy(c).to(dev) for c in S.cotangents(W, H, seed=12)]
         gb = Hh.run_ours_backward(d, cam, 3, bg_t, ours, cot, kernel_size=ks)
+        gbs = [gb] + [Hh.run_ours_backward(d, cam, 3, bg_t, ours, cot, kernel_size=ks) for _ in range(2)]     # this library's reductions are unordered too
         r1 = [Hh.run_ref_backward(d, cam, 3, bg_t, ref, cot, kernel_size=ks) for _ in range(3)]
-        Hh.adjudicate_gradients(d, cam, 3, bg_t, ri, ref["alpha"], ref["radii"], cot, gb, r1, f"needles[k={ks}]",
+        Hh.adjudicate_gradients(d, cam, 3, bg_t, ri, ref["alpha"], ref["radii"], cot, gbs, r1, f"needles[k={ks}]",
                                 kernel_size=ks)
 
 
