@@ -194,3 +194,20 @@ def test_cta_sort_with_register_bitonic_merges(VT, T):
     W = VT * T
     phys = [i + (i >> 4) for i in range(W)]
     assert len(set(phys)) == W and max(phys) < W + W // 16
+
+
+@pytest.mark.parametrize("VT", [4, 8, 16])
+def test_padded_buffer_is_bank_conflict_free_for_blocked_accesses(VT):
+    """Shared-memory layout of the sort buffers (key i at i + i/16, 8-byte keys, 32 four-byte banks): when the 32 lanes of
+    a warp access element j of their VT-key blocks — the register sort's stores and the merge passes' stores — every
+    16-lane half of the request (what the hardware serves per wavefront for 8-byte accesses) touches 16 different bank
+    pairs; without the pad word all lanes of a half hit the same few pairs (stride VT * 8 bytes)."""
+    def bank_pair(i, padded):
+        phys = i + (i >> 4) if padded else i
+        return phys % 16                       # 16 bank pairs of 8 bytes = one 128-byte wavefront
+    for j in range(VT):
+        for half in (range(0, 16), range(16, 32)):
+            padded = [bank_pair(lane * VT + j, True) for lane in half]
+            plain = [bank_pair(lane * VT + j, False) for lane in half]
+            assert len(set(padded)) == 16, (VT, j, padded)
+            assert len(set(plain)) == 16 // VT, (VT, j, plain)      # unpadded: a VT-way conflict in every half
