@@ -472,7 +472,11 @@ void sfgs_launch_tile_scan(const ImageLayout& im, unsigned long long capacity, c
 }
 
 // Gaussian ids below 2^24 ride in the key together with the reach mask (see scatter_keys_kernel)
-static inline bool sfgs_keys_packed(int P) { return P <= (1 << 24); }
+static inline bool sfgs_keys_packed(int P) {
+  // SFGS_KEYS_PACKED=0 forces the unpacked path (what P > 2^24 takes) so that the tests can run it on small scenes
+  static const bool allow = [] { const char* e = getenv("SFGS_KEYS_PACKED"); return !(e && e[0] == '0'); }();
+  return allow && P <= (1 << 24);
+}
 
 void sfgs_launch_scatter(const GeomLayout& g, const ImageLayout& im, const BinningLayout& b, int P,
                          unsigned long long capacity, cudaStream_t st) {

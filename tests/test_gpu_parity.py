@@ -298,6 +298,22 @@ def test_sort_class_boundaries_and_depth_ties(cuda_device, n):
     assert (ours["color"] - ref["color"]).abs().max().item() <= IMG_ATOL
 
 
+def test_unpacked_key_path_for_more_than_2p24_gaussians(cuda_device):
+    """With P > 2^24 a Gaussian id no longer fits beside the reach mask in the sort key: the scatter then writes
+    depth_bits << 32 | id and the sort kernels form the masks from the blend records at emit time.  The switch is read
+    once per process, so the indexing / size-class / long-list / needle tests are re-run in a child process with
+    SFGS_KEYS_PACKED=0 (small scenes through exactly that path)."""
+    import subprocess
+    import sys
+    if not ref_available():
+        pytest.skip("oracle/_ref not built")
+    env = dict(os.environ, SFGS_KEYS_PACKED="0")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-m", "gpu", "-x", "-q", "-k",
+                        "indexing or boundaries or long_tile or needles"], env=env, capture_output=True, text=True,
+                       timeout=900, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+
+
 def test_full_size_properties(cuda_device):
     """BASELINE configs[1] size (1M Gaussians, 1080p): size-independent invariants."""
     dev = cuda_device
